@@ -1,0 +1,179 @@
+"""ctypes binding of oracle/_ref/libssref_<cfg>.so — TEST INFRASTRUCTURE ONLY.
+
+The library holds the reference's own generated CPU kernels plus our thin
+wrapper restatement (oracle/ref_harness.cpp, built by oracle/build_ref.py).
+Arrays cross this boundary in the LOGICAL layout of oracle/aderdg.py
+([n,B,9]); conversion to the reference's padded column-major layout happens here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import aderdg as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def available(cfg):
+    return os.path.exists(os.path.join(HERE, "_ref", f"libssref_{cfg}.so"))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class RefLib:
+    def __init__(self, cfg):
+        path = os.path.join(HERE, "_ref", f"libssref_{cfg}.so")
+        self.lib = ctypes.CDLL(path)
+        info = np.zeros(8, dtype=np.int64)
+        self.lib.ssref_info(_p(info))
+        self.order, size, self.qsize, self.isize, self.dersize, self.qinterp, self.B, self.ld = \
+            [int(x) for x in info]
+        self.dtype = np.float32 if size == 4 else np.float64
+        offs = np.zeros(self.order, dtype=np.int64)
+        sizes = np.zeros(self.order, dtype=np.int64)
+        self.lib.ssref_der_layout(_p(offs), _p(sizes))
+        self.der_offsets, self.der_sizes = offs, sizes
+        self.lib.ssref_proxy.restype = ctypes.c_double
+        self.ppad = self.qinterp // 9
+
+    # -- layout helpers
+    def to_ref(self, x):
+        return O.to_ref_layout(np.ascontiguousarray(x, dtype=self.dtype), self.ld)
+
+    def from_ref(self, x):
+        return O.from_ref_layout(x, self.B, self.ld)
+
+    def ders_to_ref(self, ders):
+        n = ders[0].shape[0]
+        out = np.zeros((n, self.dersize), dtype=self.dtype)
+        for d, dq in enumerate(ders):
+            ld = int(self.der_sizes[d]) // 9
+            rows = min(ld, O.nbasis(self.order - d))
+            blk = np.zeros((n, 9, ld), dtype=self.dtype)
+            blk[:, :, :rows] = dq[:, :rows, :].transpose(0, 2, 1)
+            out[:, self.der_offsets[d]:self.der_offsets[d] + 9 * ld] = blk.reshape(n, -1)
+        return out
+
+    def ders_from_ref(self, x):
+        n = x.shape[0]
+        ders = []
+        for d in range(self.order):
+            ld = int(self.der_sizes[d]) // 9
+            rows = O.nbasis(self.order - d)
+            blk = x[:, self.der_offsets[d]:self.der_offsets[d] + 9 * ld].reshape(n, 9, ld)
+            dq = np.zeros((n, self.B, 9), dtype=self.dtype)
+            dq[:, :rows] = blk[:, :, :rows].transpose(0, 2, 1)
+            ders.append(dq)
+        return ders
+
+    def flops(self):
+        nz = np.zeros(55, dtype=np.int64)
+        hw = np.zeros(55, dtype=np.int64)
+        self.lib.ssref_flops(_p(nz), _p(hw))
+        return {"derivative": (int(nz[0]), int(hw[0])), "volume": (int(nz[1]), int(hw[1])),
+                "localFlux": (nz[2:6].copy(), hw[2:6].copy()),
+                "neighboringFlux": (nz[6:54].copy(), hw[6:54].copy()),
+                "taylor": (int(nz[54]), int(hw[54]))}
+
+    # -- kernels (logical layout in/out)
+    def ader(self, Q, star, coeffs, want_derivatives=False):
+        n = Q.shape[0]
+        q = self.to_ref(Q)
+        I = np.zeros((n, self.isize), dtype=self.dtype)
+        der = np.zeros((n, self.dersize), dtype=self.dtype) if want_derivatives else None
+        c = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        s = np.ascontiguousarray(star, dtype=self.dtype)
+        self.lib.ssref_ader(ctypes.c_int64(n), _p(c), _p(q), _p(s), _p(I), _p(der))
+        if want_derivatives:
+            return self.from_ref(I), self.ders_from_ref(der)
+        return self.from_ref(I)
+
+    def taylor(self, ders, coeffs):
+        n = ders[0].shape[0]
+        der = self.ders_to_ref(ders)
+        I = np.zeros((n, self.isize), dtype=self.dtype)
+        c = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        self.lib.ssref_taylor(ctypes.c_int64(n), _p(c), _p(der), _p(I))
+        return self.from_ref(I)
+
+    def local(self, Q, I, star, Aplus, face_types):
+        n = Q.shape[0]
+        q, i = self.to_ref(Q), self.to_ref(I)
+        s = np.ascontiguousarray(star, dtype=self.dtype)
+        a = np.ascontiguousarray(Aplus, dtype=self.dtype)
+        ft = np.ascontiguousarray(face_types, dtype=np.uint8)
+        self.lib.ssref_local(ctypes.c_int64(n), _p(q), _p(i), _p(s), _p(a), _p(ft))
+        return self.from_ref(q)
+
+    def neighbor(self, Q, Iall, neighbors, Aminus, face_rel, face_types, dr=None):
+        n = Q.shape[0]
+        q, i = self.to_ref(Q), self.to_ref(Iall)
+        a = np.ascontiguousarray(Aminus, dtype=self.dtype)
+        nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+        fr = np.ascontiguousarray(face_rel, dtype=np.uint8)
+        ft = np.ascontiguousarray(face_types, dtype=np.uint8)
+        if dr is None:
+            args = [None] * 5
+        else:
+            god = self.points_to_ref(dr["godunov"])
+            fs = np.ascontiguousarray(dr["fluxSolver"].transpose(0, 2, 1), dtype=self.dtype)
+            args = [god, fs, np.ascontiguousarray(dr["index"], dtype=np.int64),
+                    np.ascontiguousarray(dr["side"], dtype=np.uint8),
+                    np.ascontiguousarray(dr["rel"], dtype=np.uint8)]
+        self.lib.ssref_neigh(ctypes.c_int64(n), _p(q), _p(i), _p(nb), _p(a), _p(fr), _p(ft),
+                             *[_p(x) for x in args])
+        return self.from_ref(q)
+
+    def points_to_ref(self, x):
+        """[m, P, 9] -> [m, 9*Ppad] (point fastest)."""
+        m, P, _ = x.shape
+        out = np.zeros((m, 9, self.ppad), dtype=self.dtype)
+        out[:, :, :P] = x.transpose(0, 2, 1)
+        return out.reshape(m, -1)
+
+    def dr_interpolate(self, ders_plus, ders_minus, tinvT, face_info, coeffs):
+        n = ders_plus[0].shape[0]
+        P = (self.order + 1) ** 2
+        dp, dm = self.ders_to_ref(ders_plus), self.ders_to_ref(ders_minus)
+        # TinvT dense [n,9(q),9(p)] -> column-major TinvT[q + 9p]
+        t = np.ascontiguousarray(tinvT.transpose(0, 2, 1), dtype=self.dtype)
+        fi = np.ascontiguousarray(face_info, dtype=np.uint8)
+        c = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        qp = np.zeros((n, self.order, self.qinterp), dtype=self.dtype)
+        qm = np.zeros_like(qp)
+        self.lib.ssref_dr_interp(ctypes.c_int64(n), _p(dp), _p(dm), _p(t), _p(fi), _p(c),
+                                 _p(qp), _p(qm))
+        conv = lambda x: np.ascontiguousarray(
+            x.reshape(n, self.order, 9, self.ppad)[:, :, :, :P].transpose(0, 1, 3, 2))
+        return conv(qp), conv(qm)
+
+    def resample(self, x):
+        n, P = x.shape
+        xin = np.zeros((n, self.ppad), dtype=self.dtype)
+        xin[:, :P] = x
+        out = np.zeros_like(xin)
+        self.lib.ssref_resample(ctypes.c_int64(n), _p(xin), _p(out))
+        return out[:, :P]
+
+    def proxy(self, kernel, d, coeffs, steps):
+        """Timed proxy passes on reference-layout copies; returns (seconds, Q, I)."""
+        kid = {"all": 0, "local": 1, "neigh": 2, "ader": 3, "localwoader": 4}[kernel]
+        n = d["Q"].shape[0]
+        q = self.to_ref(d["Q"])
+        buf = self.to_ref(d["I"]) if "I" in d else np.zeros((n, self.isize), dtype=self.dtype)
+        c = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        arrs = [np.ascontiguousarray(d["star"], dtype=self.dtype),
+                np.ascontiguousarray(d["Aplus"], dtype=self.dtype),
+                np.ascontiguousarray(d["Aminus"], dtype=self.dtype),
+                np.ascontiguousarray(d["neighbors"], dtype=np.int64),
+                np.ascontiguousarray(d["face_rel"], dtype=np.uint8),
+                np.ascontiguousarray(d["face_types"], dtype=np.uint8)]
+        t = self.lib.ssref_proxy(ctypes.c_int(kid), ctypes.c_int64(n), ctypes.c_int(steps), _p(c),
+                                 _p(q), _p(buf), *[_p(a) for a in arrs])
+        return t, self.from_ref(q), self.from_ref(buf)
+
+    def threads(self):
+        return int(self.lib.ssref_threads())
