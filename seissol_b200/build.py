@@ -1,0 +1,86 @@
+"""Build libseissol_b200.so in-tree (seissol_b200/lib/), sm_100a only.
+
+Steps: (1) regenerate the immediate-operand operator code (codegen/gen_ops.py),
+(2) compile every translation unit under csrc/ with
+`nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo` in parallel,
+(3) link the shared library.  Objects are rebuilt only when a source is newer.
+"""
+import glob
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "..", "build", "obj")
+LIB = os.path.join(LIBDIR, "libseissol_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(verbose=True, force=False, extra_flags=()):
+    sys.path.insert(0, os.path.join(HERE, "codegen"))
+    import gen_ops  # noqa: E402
+
+    os.makedirs(gen_ops.OUTDIR, exist_ok=True)
+    for o in (4, 5, 6):
+        text, _ = gen_ops.generate(o)
+        path = os.path.join(gen_ops.OUTDIR, f"ops_o{o}.cuh")
+        if not os.path.exists(path) or open(path).read() != text:
+            open(path, "w").write(text)
+    extra = sorted(glob.glob(os.path.join(HERE, "codegen", "gen_*.py")))
+    for mod in extra:
+        name = os.path.splitext(os.path.basename(mod))[0]
+        if name != "gen_ops":
+            m = __import__(name)
+            if hasattr(m, "emit_all"):
+                m.emit_all()
+
+    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        glob.glob(os.path.join(CSRC, "gen", "*.cuh")) + \
+        glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    jobs = []
+    for src in sources:
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        if force or _newer(obj, [src] + headers):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = ["nvcc", *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[build] compiled {os.path.basename(src)}", flush=True)
+        return obj
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o") for s in sources]
+    if jobs or not os.path.exists(LIB):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[build] linked {LIB}", flush=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

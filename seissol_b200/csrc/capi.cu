@@ -1,0 +1,287 @@
+// C ABI of libseissol_b200.so (declared in include/seissol_b200.h).  Thin argument
+// validation + dispatch onto the per-(order, real) kernel instantiations.  No CPU path.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/seissol_b200.h"
+#include "api_internal.h"
+
+using namespace ssb;
+
+struct ssb_ctx {
+  const KernelSet* ks;
+  int order;
+  int realSize;
+  int equation;
+  int ldq;
+  int derOffset[8];
+  int derLd[8];
+  int derSize;
+};
+
+namespace {
+
+int basisFunctions(int order) { return order * (order + 1) * (order + 2) / 6; }
+
+void compactLayout(ssb_ctx* c) {
+  c->ldq = (basisFunctions(c->order) + 3) / 4 * 4;
+  int off = 0;
+  for (int d = 0; d < c->order; ++d) {
+    const int ld = (basisFunctions(c->order - d) + 3) / 4 * 4;
+    c->derOffset[d] = off;
+    c->derLd[d] = ld;
+    off += 9 * ld;
+  }
+  c->derSize = off;
+}
+
+void referenceLayout(ssb_ctx* c) {
+  const int per = 64 / c->realSize;  // 64-byte aligned leading dimensions
+  auto align = [&](int rows) { return (rows + per - 1) / per * per; };
+  c->ldq = align(basisFunctions(c->order));
+  int off = 0;
+  for (int d = 0; d < c->order; ++d) {
+    const int ld = align(basisFunctions(c->order - d));
+    c->derOffset[d] = off;
+    c->derLd[d] = ld;
+    off += 9 * ld;
+  }
+  c->derSize = off;
+}
+
+ElemArray conv(const ssb_array_t& a) {
+  ElemArray r;
+  r.ptrs = a.ptrs;
+  r.base = static_cast<const char*>(a.base);
+  r.strideBytes = a.stride_bytes;
+  return r;
+}
+
+const KernelSet* lookup(int order, int realSize) {
+  if (realSize == 4) {
+    switch (order) {
+      case 4: return kernelset_o4_f32();
+      case 5: return kernelset_o5_f32();
+      case 6: return kernelset_o6_f32();
+      default: return nullptr;
+    }
+  }
+  if (realSize == 8) {
+    switch (order) {
+      case 4: return kernelset_o4_f64();
+      case 5: return kernelset_o5_f64();
+      case 6: return kernelset_o6_f64();
+      default: return nullptr;
+    }
+  }
+  return nullptr;
+}
+
+int fillLocal(ssb_ctx* c, LocalParams& p, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs,
+              ssb_array_t localInt, const uint8_t* faceTypes, const double* coeffs, long long n,
+              const int* perm) {
+  if (c == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  p.idofs = conv(idofs);
+  p.derivs = conv(derivs);
+  p.localInt = conv(localInt);
+  if (!p.dofs.present() || !p.idofs.present() || !p.localInt.present()) {
+    return SSB_EINVAL;
+  }
+  p.faceTypes = faceTypes;
+  p.perm = perm;
+  p.n = n;
+  p.ldg = c->ldq;
+  for (int d = 0; d < c->order; ++d) {
+    p.derOffset[d] = c->derOffset[d];
+    p.derLd[d] = c->derLd[d];
+    p.coeffs[d] = coeffs != nullptr ? coeffs[d] : 0.0;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechanisms) {
+  if (out == nullptr) {
+    return SSB_EINVAL;
+  }
+  *out = nullptr;
+  if (equation != 0 || mechanisms != 0) {
+    return SSB_EUNSUPPORTED;
+  }
+  const KernelSet* ks = lookup(order, real_size);
+  if (ks == nullptr) {
+    return SSB_EUNSUPPORTED;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return SSB_ENODEVICE;
+  }
+  ssb_ctx* c = new (std::nothrow) ssb_ctx();
+  if (c == nullptr) {
+    return SSB_EINVAL;
+  }
+  c->ks = ks;
+  c->order = order;
+  c->realSize = real_size;
+  c->equation = equation;
+  compactLayout(c);
+  *out = c;
+  return 0;
+}
+
+void ssb_destroy(ssb_ctx* c) { delete c; }
+
+int ssb_set_layout(ssb_ctx* c, int ld_q, const int* der_offset, const int* der_ld) {
+  if (c == nullptr || ld_q < c->ks->BP || ld_q % 4 != 0) {
+    return SSB_EINVAL;
+  }
+  c->ldq = ld_q;
+  if (der_offset != nullptr && der_ld != nullptr) {
+    int end = 0;
+    for (int d = 0; d < c->order; ++d) {
+      if (der_ld[d] % 4 != 0 || der_offset[d] % 4 != 0 || der_ld[d] < (basisFunctions(c->order - d) + 3) / 4 * 4) {
+        return SSB_EINVAL;
+      }
+      c->derOffset[d] = der_offset[d];
+      c->derLd[d] = der_ld[d];
+      end = der_offset[d] + 9 * der_ld[d] > end ? der_offset[d] + 9 * der_ld[d] : end;
+    }
+    c->derSize = end;
+  }
+  return 0;
+}
+
+int ssb_layout_reference(ssb_ctx* c) {
+  if (c == nullptr) {
+    return SSB_EINVAL;
+  }
+  referenceLayout(c);
+  return 0;
+}
+
+int ssb_query(const ssb_ctx* c, int* out) {
+  if (c == nullptr || out == nullptr) {
+    return SSB_EINVAL;
+  }
+  std::memset(out, 0, 24 * sizeof(int));
+  out[0] = c->ks->B;
+  out[1] = c->ldq;
+  out[2] = 9 * c->ldq;
+  out[3] = c->derSize;
+  for (int d = 0; d < c->order; ++d) {
+    out[4 + d] = c->derOffset[d];
+    out[12 + d] = c->derLd[d];
+  }
+  out[20] = c->ks->eLocal;
+  out[21] = c->ks->eNeigh;
+  return 0;
+}
+
+int ssb_ader(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs, ssb_array_t local_int,
+             const double* coeffs, long long n, const int* perm, void* stream) {
+  LocalParams p;
+  if (coeffs == nullptr) {
+    return SSB_EINVAL;
+  }
+  const int rc = fillLocal(c, p, dofs, idofs, derivs, local_int, nullptr, coeffs, n, perm);
+  if (rc != 0) {
+    return rc;
+  }
+  return c->ks->local(p, true, false, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t local_int,
+              const uint8_t* face_types, long long n, const int* perm, void* stream) {
+  LocalParams p;
+  ssb_array_t none = {nullptr, nullptr, 0};
+  const int rc = fillLocal(c, p, dofs, idofs, none, local_int, face_types, nullptr, n, perm);
+  if (rc != 0) {
+    return rc;
+  }
+  return c->ks->local(p, false, true, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_ader_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs,
+                   ssb_array_t local_int, const uint8_t* face_types, const double* coeffs, long long n,
+                   const int* perm, void* stream) {
+  LocalParams p;
+  if (coeffs == nullptr) {
+    return SSB_EINVAL;
+  }
+  const int rc = fillLocal(c, p, dofs, idofs, derivs, local_int, face_types, coeffs, n, perm);
+  if (rc != 0) {
+    return rc;
+  }
+  return c->ks->local(p, true, true, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* coeffs, long long n,
+               void* stream) {
+  if (c == nullptr || coeffs == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  TaylorParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.derivs = conv(derivs);
+  p.idofs = conv(idofs);
+  if (!p.derivs.present() || !p.idofs.present()) {
+    return SSB_EINVAL;
+  }
+  p.n = n;
+  p.ldg = c->ldq;
+  p.order = c->order;
+  for (int d = 0; d < c->order; ++d) {
+    p.rows[d] = basisFunctions(c->order - d);
+    p.derOffset[d] = c->derOffset[d];
+    p.derLd[d] = c->derLd[d];
+    p.coeffs[d] = coeffs[d];
+  }
+  return c->ks->taylor(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
+              ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types, const uint8_t* face_rel,
+              long long n, const int* perm, void* stream) {
+  if (c == nullptr || n < 0 || face_rel == nullptr) {
+    return SSB_EINVAL;
+  }
+  NeighParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  p.neighInt = conv(neigh_int);
+  p.idofs = conv(idofs);
+  p.nbPtrs = nb_ptrs;
+  p.nbIdx = nb_idx;
+  if (!p.dofs.present() || !p.neighInt.present() ||
+      (nb_ptrs == nullptr && (nb_idx == nullptr || !p.idofs.present()))) {
+    return SSB_EINVAL;
+  }
+  p.faceTypes = face_types;
+  p.faceRel = face_rel;
+  p.perm = perm;
+  p.n = n;
+  p.ldg = c->ldq;
+  return c->ks->neigh(p, static_cast<cudaStream_t>(stream));
+}
+
+const char* ssb_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case SSB_EINVAL: return "invalid argument";
+    case SSB_EUNSUPPORTED: return "configuration (order, precision, equation) not compiled in";
+    case SSB_ENODEVICE: return "no CUDA device available (there is no CPU fallback)";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+const char* ssb_version(void) { return "seissol_b200 0.1 (sm_100a)"; }
+}

@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference proxy (src/Proxy, app/Proxy) on top of the C ABI.
+
+Same kernel names (`all, local, neigh, ader, localwoader, ...`; src/Proxy/Common.cpp:33-40),
+same composition (`all = local ∘ neigh`, `local = ader ∘ localwoader` fused;
+src/Proxy/KernelHost.h:29-56), same timing protocol (one untimed warm-up pass, then
+`timesteps` timed passes; src/Proxy/Runner.cpp:93-111) and the same output fields
+(src/Proxy/Common.cpp:91-151).  Data lives in torch CUDA tensors in the device layout
+described in DESIGN.md §2; all arithmetic happens in libseissol_b200.so.
+"""
+import math
+import time
+
+import numpy as np
+
+from . import api
+
+KERNEL_NAMES = ["all", "local", "neigh", "ader", "localwoader", "neigh_dr", "godunov_dr", "all_dr"]
+TIMESTEP = 1.0  # src/Proxy/Constants.h
+
+# Static non-zero / hardware flop counts per element, read from the reference's generated
+# kernels (`kernel::X::NonZeroFlops/HardwareFlops`, Monitoring/Metric.h:54-59) with
+# oracle/ref_lib.py::RefLib.flops(); neighboringFlux is the mean over the 48 relations
+# (uniform (h,j) as drawn by the proxy, src/Proxy/Allocator.cpp:67-87).
+FLOPS = {
+    4: {"derivative": (6642, 34146), "volume": (4806, 19584), "localFlux": (18972, None),
+        "neighboringFlux": (4 * 5073.0, None)},
+    6: {"derivative": (56286, 248292), "volume": (34839, 127872), "localFlux": (79200, 246528),
+        "neighboringFlux": (4 * 20805.0, 4 * 73728)},
+}
+
+
+def nbasis(order):
+    return order * (order + 1) * (order + 2) // 6
+
+
+def integrate_coeffs(order, t0, t1):
+    """MonomialBasis::integrate (src/Numerical/TimeBasis.h:82-96)."""
+    return np.array([(t1 ** (d + 1) - t0 ** (d + 1)) / math.factorial(d + 1) for d in range(order)])
+
+
+def nz_flops_per_element(order, kernel):
+    f = FLOPS[order]
+    ader = f["derivative"][0]
+    lwo = f["volume"][0] + f["localFlux"][0]
+    neigh = f["neighboringFlux"][0]
+    return {"ader": ader, "localwoader": lwo, "local": ader + lwo, "neigh": neigh,
+            "all": ader + lwo + neigh}[kernel]
+
+
+def algorithmic_bytes_per_element(order, real_size, kernel):
+    """unpadded reals x sizeof(real); constants and indices excluded."""
+    bq = nbasis(order) * 9
+    s, a = 72, 81
+    reals = {"ader": 2 * bq + s, "localwoader": 3 * bq + s + 4 * a, "local": 3 * bq + s + 4 * a,
+             "neigh": 6 * bq + 4 * a, "all": 9 * bq + s + 8 * a}[kernel]
+    return reals * real_size
+
+
+class ProxyData:
+    """Fake single-layer storage, as ProxyData/fakeData (src/Proxy/Allocator.cpp:49-134)
+    but with bounded values.  Device layout: dofs/buffers [n, 9, ld]
+    column-major per element; local_int [n, 396] = star[3][24] | nApNm1[4][81];
+    neigh_int [n, 324] = nAmNm1[4][81]."""
+
+    def __init__(self, ctx, cells, device="cuda:0"):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.cells = cells
+        self.device = torch.device(device)
+        self.dtype = torch.float32 if ctx.real_size == 4 else torch.float64
+        self.np_dtype = np.float32 if ctx.real_size == 4 else np.float64
+        self.perm = None
+
+    # -- construction ---------------------------------------------------------------
+    @classmethod
+    def from_host(cls, ctx, d, device="cuda:0"):
+        """d: dict of numpy arrays in the oracle's logical layout (oracle/aderdg.py::proxy_data)."""
+        self = cls(ctx, d["Q"].shape[0], device)
+        t = self.torch
+        self.dofs = self.to_device_layout(d["Q"])
+        self.buffers = (self.to_device_layout(d["I"]) if "I" in d
+                        else t.zeros_like(self.dofs))
+        li = np.concatenate([d["star"].reshape(self.cells, 72), d["Aplus"].reshape(self.cells, 324)], axis=1)
+        self.local_int = t.from_numpy(np.ascontiguousarray(li, dtype=self.np_dtype)).to(self.device)
+        self.neigh_int = t.from_numpy(np.ascontiguousarray(d["Aminus"].reshape(self.cells, 324),
+                                                           dtype=self.np_dtype)).to(self.device)
+        self.face_rel = t.from_numpy(np.ascontiguousarray(d["face_rel"], dtype=np.uint8)).to(self.device)
+        self.face_types = t.from_numpy(np.ascontiguousarray(d["face_types"], dtype=np.uint8)).to(self.device)
+        self.neighbors = t.from_numpy(np.ascontiguousarray(d["neighbors"], dtype=np.int64)).to(self.device)
+        return self
+
+    @classmethod
+    def synthetic(cls, ctx, cells, device="cuda:0", seed=42, scale=1e-2):
+        """Bounded synthetic data generated on the device (large problem sizes)."""
+        self = cls(ctx, cells, device)
+        t = self.torch
+        g = t.Generator(device=self.device)
+        g.manual_seed(seed)
+        ld, B = ctx.ld, ctx.B
+        q = t.rand((cells, 9, ld), generator=g, device=self.device, dtype=self.dtype) * 2 - 1
+        if ld > B:
+            q[:, :, B:] = 0
+        self.dofs = q.reshape(cells, 9 * ld).contiguous()
+        self.buffers = t.zeros_like(self.dofs)
+        self.local_int = ((t.rand((cells, 396), generator=g, device=self.device, dtype=self.dtype) * 2 - 1)
+                          * scale).contiguous()
+        self.neigh_int = ((t.rand((cells, 324), generator=g, device=self.device, dtype=self.dtype) * 2 - 1)
+                          * scale).contiguous()
+        rel = t.empty((cells, 4, 2), dtype=t.uint8, device=self.device)
+        rel[:, :, 0] = t.randint(0, 4, (cells, 4), generator=g, device=self.device).to(t.uint8)
+        rel[:, :, 1] = t.randint(0, 3, (cells, 4), generator=g, device=self.device).to(t.uint8)
+        self.face_rel = rel.contiguous()
+        self.face_types = t.zeros((cells, 4), dtype=t.uint8, device=self.device)
+        self.neighbors = t.randint(0, cells, (cells, 4), generator=g, device=self.device, dtype=t.int64)
+        return self
+
+    # -- layouts ----------------------------------------------------------------------
+    def to_device_layout(self, x):
+        n, b, q = x.shape
+        out = np.zeros((n, q, self.ctx.ld), dtype=self.np_dtype)
+        out[:, :, :b] = x.transpose(0, 2, 1)
+        return self.torch.from_numpy(out.reshape(n, q * self.ctx.ld)).to(self.device)
+
+    def to_logical(self, t):
+        x = t.detach().cpu().numpy().reshape(t.shape[0], 9, self.ctx.ld)
+        return np.ascontiguousarray(x[:, :, :self.ctx.B].transpose(0, 2, 1))
+
+    def sort_by_face_relation(self):
+        """Processing order that makes the neighbor's face id j uniform per CTA for all four
+        faces (256 classes), removing warp divergence in the rT_j selection of k_neigh.
+        This is our analogue of the reference's recorder grouping by ConditionalKey
+        (src/Initializer/BatchRecorders/NeighIntegrationRecorder.cpp:142-144)."""
+        t = self.torch
+        j = self.face_rel[:, :, 0].to(t.int64)
+        key = j[:, 0] + 4 * j[:, 1] + 16 * j[:, 2] + 64 * j[:, 3]
+        self.perm = t.argsort(key, stable=True).to(t.int32).contiguous()
+        return self.perm
+
+    def bytes_resident(self):
+        return sum(x.numel() * x.element_size() for x in
+                   (self.dofs, self.buffers, self.local_int, self.neigh_int, self.face_rel,
+                    self.face_types, self.neighbors))
+
+
+class ProxyKernels:
+    """Kernel-name dispatch (getProxyKernelDevice, src/Proxy/KernelDevice.cpp:126-150)."""
+
+    def __init__(self, ctx, data):
+        self.ctx, self.d = ctx, data
+        self.coeffs = integrate_coeffs(ctx.order, 0.0, TIMESTEP)
+
+    def ader(self, stream=None):
+        d = self.d
+        self.ctx.ader(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
+                      self.coeffs, d.cells, stream=stream)
+
+    def localwoader(self, stream=None):
+        d = self.d
+        self.ctx.local(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.local_int),
+                       d.face_types, d.cells, stream=stream)
+
+    def local(self, stream=None):
+        d = self.d
+        self.ctx.ader_local(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
+                            d.face_types, self.coeffs, d.cells, stream=stream)
+
+    def neigh(self, stream=None):
+        d = self.d
+        self.ctx.neigh(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.neigh_int),
+                       d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
+
+    def all(self, stream=None):
+        self.local(stream)
+        self.neigh(stream)
+
+    def run(self, name, stream=None):
+        for part in name.split(","):
+            getattr(self, part)(stream)
+
+    def launches(self, name):
+        return sum({"all": 2, "local": 1, "neigh": 1, "ader": 1, "localwoader": 1}[p] for p in name.split(","))
+
+
+def run_proxy(order, real_size, cells, timesteps, kernel, device="cuda:0", data=None, sort=True):
+    """runProxy (src/Proxy/Runner.cpp:57-151): returns the reference's output fields plus
+    element-updates/s."""
+    import torch
+    ctx = api.Context(order, real_size)
+    d = data if data is not None else ProxyData.synthetic(ctx, cells, device)
+    if sort and d.perm is None:
+        d.sort_by_face_relation()
+    k = ProxyKernels(ctx, d)
+    k.run(kernel)  # warm-up pass (Runner.cpp:93-95)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(timesteps):
+        k.run(kernel)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    nz = sum(nz_flops_per_element(order, p) for p in kernel.split(",")) * cells * timesteps
+    by = sum(algorithmic_bytes_per_element(order, real_size, p) for p in kernel.split(",")) * cells * timesteps
+    return {
+        "name": kernel, "time": dt, "cycles": 0.0,
+        "gflop-nz": nz * 1e-9, "gib": by / 2 ** 30,
+        "gflops-nz": nz * 1e-9 / dt, "gibs": by / 2 ** 30 / dt,
+        "elem-updates-per-s": cells * timesteps / dt,
+    }

@@ -1,0 +1,212 @@
+"""GPU parity tests (run with -m gpu): the sm_100a kernels, called through the C ABI, against
+the CPU oracle on identical seeded inputs.  Tolerances are BASELINE.json's: relative L2 of
+the DOFs <= 1e-5 (single) / 1e-11 (double) after N time steps; single kernels are held
+to a tighter 100*eps-class bound."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import aderdg as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CONFIGS = [(4, np.float32), (5, np.float32), (6, np.float32), (4, np.float64), (6, np.float64)]
+
+
+def step_tol(dt):
+    return 2e-6 if dt == np.float32 else 5e-15
+
+
+def run_tol(dt):
+    return 1e-5 if dt == np.float32 else 1e-11
+
+
+@pytest.fixture(scope="module")
+def gpu(built_library):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    from seissol_b200 import api, proxy
+    return torch, api, proxy
+
+
+def make(order, dt, n, api, proxy, seed=5, reference_layout=False):
+    ctx = api.Context(order, np.dtype(dt).itemsize, reference_layout=reference_layout)
+    host = O.proxy_data(order, n, dt, seed=seed)
+    data = proxy.ProxyData.from_host(ctx, host)
+    return ctx, host, data, O.load_tables(order, dt), O.time_integrate_coeffs(order, 0.0, 1.0, dt)
+
+
+@pytest.mark.parametrize("order,dt", CONFIGS)
+def test_ader_with_derivatives(gpu, order, dt):
+    torch, api, proxy = gpu
+    n = 333  # ragged: not a multiple of the elements-per-CTA tile
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy)
+    ders_dev = torch.zeros((n, ctx.dersize), dtype=data.dtype, device=data.device)
+    ctx.ader(api.strided(data.dofs), api.strided(data.buffers), api.strided(ders_dev),
+             api.strided(data.local_int), c, n)
+    torch.cuda.synchronize()
+    star = O.star_dense(host["star"], tab["star_pattern"])
+    I, ders = O.ader(tab, host["Q"], star, c, True)
+    assert rel_l2(data.to_logical(data.buffers), I) < step_tol(dt)
+    assert rel_l2(data.to_logical(data.dofs), host["Q"]) == 0.0  # ader must not touch Q
+    dd = ders_dev.cpu().numpy()
+    for d in range(order):
+        rows = O.nbasis(order - d)
+        blk = dd[:, ctx.der_offset[d]:ctx.der_offset[d] + 9 * ctx.der_ld[d]].reshape(n, 9, ctx.der_ld[d])
+        assert rel_l2(blk[:, :, :rows].transpose(0, 2, 1), ders[d][:, :rows]) < step_tol(dt)
+    # Taylor sum of the stored family over a sub-interval (LTS neighbor path)
+    c2 = O.time_integrate_coeffs(order, 0.25, 0.75, dt)
+    out = torch.zeros_like(data.buffers)
+    ctx.taylor(api.strided(ders_dev), api.strided(out), c2, n)
+    torch.cuda.synchronize()
+    assert rel_l2(data.to_logical(out), O.taylor(ders, c2)) < step_tol(dt)
+
+
+@pytest.mark.parametrize("order,dt", CONFIGS)
+def test_localwoader_and_fused_local(gpu, order, dt):
+    torch, api, proxy = gpu
+    n = 200
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=9)
+    host["face_types"][5, 2] = 3   # DynamicRupture faces get no local flux
+    host["face_types"][17, 0] = 3
+    data = proxy.ProxyData.from_host(ctx, host)
+    star = O.star_dense(host["star"], tab["star_pattern"])
+    I = O.ader(tab, host["Q"], star, c)
+    want = O.local(tab, host["Q"], I, star, O.flux_dense(host["Aplus"]), host["face_types"])
+    # fused ader+local
+    k = proxy.ProxyKernels(ctx, data)
+    k.local()
+    torch.cuda.synchronize()
+    assert rel_l2(data.to_logical(data.buffers), I) < step_tol(dt)
+    assert rel_l2(data.to_logical(data.dofs), want) < step_tol(dt)
+    assert rel_l2(data.to_logical(data.dofs) - host["Q"], want - host["Q"]) < 50 * step_tol(dt)
+    # stand-alone localwoader on the oracle's I
+    host2 = dict(host)
+    host2["I"] = I
+    data2 = proxy.ProxyData.from_host(ctx, host2)
+    proxy.ProxyKernels(ctx, data2).localwoader()
+    torch.cuda.synchronize()
+    assert rel_l2(data2.to_logical(data2.dofs), want) < step_tol(dt)
+
+
+@pytest.mark.parametrize("order,dt", CONFIGS)
+@pytest.mark.parametrize("sort", [False, True])
+def test_neighbor(gpu, order, dt, sort):
+    torch, api, proxy = gpu
+    n = 301
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=13)
+    rng = np.random.default_rng(0)
+    host["I"] = rng.uniform(-1, 1, host["Q"].shape).astype(dt)
+    host["face_types"][3, 1] = 1   # free surface: no neighbor contribution
+    host["face_types"][8, 3] = 5   # outflow
+    data = proxy.ProxyData.from_host(ctx, host)
+    if sort:
+        data.sort_by_face_relation()
+    proxy.ProxyKernels(ctx, data).neigh()
+    torch.cuda.synchronize()
+    want = O.neighbor(tab, host["Q"], host["I"], host["neighbors"], O.flux_dense(host["Aminus"]),
+                      host["face_rel"], host["face_types"])
+    assert rel_l2(data.to_logical(data.dofs), want) < step_tol(dt)
+    assert rel_l2(data.to_logical(data.dofs) - host["Q"], want - host["Q"]) < 50 * step_tol(dt)
+
+
+@pytest.mark.parametrize("order,dt", [(6, np.float32), (6, np.float64), (4, np.float32)])
+def test_all_n_steps(gpu, order, dt):
+    """BASELINE.json parity bar: DOFs after N steps of `all` within 1e-5 (f32) / 1e-11 (f64)."""
+    torch, api, proxy = gpu
+    n, steps = 2000, 10
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=21)
+    data.sort_by_face_relation()
+    k = proxy.ProxyKernels(ctx, data)
+    for _ in range(steps):
+        k.all()
+        host = O.proxy_step(tab, host, c, "all")
+    torch.cuda.synchronize()
+    err = rel_l2(data.to_logical(data.dofs), host["Q"])
+    assert np.isfinite(err) and err < run_tol(dt), err
+    assert rel_l2(data.to_logical(data.buffers), host["I"]) < run_tol(dt)
+
+
+@pytest.mark.parametrize("cfg,order,dt", [("elastic_o4_f32", 4, np.float32), ("elastic_o6_f32", 6, np.float32),
+                                          ("elastic_o6_f64", 6, np.float64)])
+def test_against_reference_golden_vectors(gpu, cfg, order, dt):
+    """Outputs of the REFERENCE's generated kernels (tests/golden) on the same inputs."""
+    torch, api, proxy = gpu
+    g = dict(np.load(os.path.join(GOLDEN, f"{cfg}.npz")))
+    ctx = api.Context(order, np.dtype(dt).itemsize)
+    n = g["Q"].shape[0]
+    data = proxy.ProxyData.from_host(ctx, {k: g[k] for k in ("Q", "star", "Aplus", "Aminus", "face_rel",
+                                                             "neighbors", "face_types")})
+    ctx.ader_local(api.strided(data.dofs), api.strided(data.buffers), None, api.strided(data.local_int),
+                   data.face_types, g["coeffs"], n)
+    torch.cuda.synchronize()
+    assert rel_l2(data.to_logical(data.buffers), g["I"]) < step_tol(dt)
+    assert rel_l2(data.to_logical(data.dofs), g["Q_local"]) < step_tol(dt)
+    ftn = torch.from_numpy(g["face_types_neigh"]).to(data.device)
+    ctx.neigh(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.neigh_int), ftn,
+              data.face_rel, n, nb_idx=data.neighbors)
+    torch.cuda.synchronize()
+    assert rel_l2(data.to_logical(data.dofs), g["Q_all"]) < step_tol(dt)
+
+
+def test_reference_layout_and_pointer_tables(gpu):
+    """Drop-in mode: the reference's 64-byte padded layout, addressed through `real**` tables
+    (ConditionalPointersToRealsTable) instead of base+stride."""
+    torch, api, proxy = gpu
+    order, dt, n = 6, np.float32, 150
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=4, reference_layout=True)
+    assert ctx.ld == 64 and ctx.der_ld[:3] == [64, 48, 32]
+
+    def table(t):
+        stride = t.stride(0) * t.element_size()
+        return api.pointer_table(t.data_ptr() + stride * torch.arange(n, device=t.device, dtype=torch.int64))
+
+    nb_ptrs = (data.buffers.data_ptr() + data.buffers.stride(0) * data.buffers.element_size()
+               * data.neighbors).contiguous()
+    ctx.ader_local(table(data.dofs), table(data.buffers), None, table(data.local_int), data.face_types, c, n)
+    ctx.neigh(table(data.dofs), api.NONE, table(data.neigh_int), data.face_types, data.face_rel, n,
+              nb_ptrs=nb_ptrs)
+    torch.cuda.synchronize()
+    want = O.proxy_step(tab, host, c, "all")
+    assert rel_l2(data.to_logical(data.dofs), want["Q"]) < step_tol(dt)
+    # padding rows stay zero
+    pad = data.dofs.reshape(n, 9, ctx.ld)[:, :, ctx.B:]
+    assert float(pad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [0, 1, 13, 14, 15])
+def test_edge_sizes(gpu, n):
+    torch, api, proxy = gpu
+    order, dt = 4, np.float32
+    ctx = api.Context(order, 4)
+    if n == 0:
+        z = torch.zeros((0, ctx.qsize), device="cuda", dtype=torch.float32)
+        ctx.ader(api.strided(z), api.strided(z), None, api.strided(z), np.ones(order), 0)
+        return
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=n)
+    proxy.ProxyKernels(ctx, data).all()
+    torch.cuda.synchronize()
+    want = O.proxy_step(tab, host, c, "all")
+    assert rel_l2(data.to_logical(data.dofs), want["Q"]) < step_tol(dt)
+
+
+def test_linearity_at_full_size(gpu):
+    """Size-independent property at BASELINE.json's full size (1M elements, O6 f32):
+    all(a*Q) == a*all(Q) up to rounding, and the result is finite."""
+    torch, api, proxy = gpu
+    ctx = api.Context(6, 4)
+    n = 1_000_000
+    d1 = proxy.ProxyData.synthetic(ctx, n, seed=1)
+    d1.sort_by_face_relation()
+    d2 = proxy.ProxyData.synthetic(ctx, n, seed=1)
+    d2.perm = d1.perm
+    d2.dofs *= 2.0
+    proxy.ProxyKernels(ctx, d1).all()
+    proxy.ProxyKernels(ctx, d2).all()
+    torch.cuda.synchronize()
+    diff = (d2.dofs - 2.0 * d1.dofs).double().norm() / d2.dofs.double().norm()
+    assert torch.isfinite(diff) and float(diff) < 1e-6
