@@ -85,6 +85,9 @@ int fillLocal(ssb_ctx* c, LocalParams& p, ssb_array_t dofs, ssb_array_t idofs, s
     return SSB_EINVAL;
   }
   std::memset(&p, 0, sizeof(p));
+  if (n == 0) {
+    return 0;  // empty batch: nothing to validate, the launcher is a no-op
+  }
   p.dofs = conv(dofs);
   p.idofs = conv(idofs);
   p.derivs = conv(derivs);
@@ -233,6 +236,9 @@ int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* 
   std::memset(&p, 0, sizeof(p));
   p.derivs = conv(derivs);
   p.idofs = conv(idofs);
+  if (n == 0) {
+    return 0;
+  }
   if (!p.derivs.present() || !p.idofs.present()) {
     return SSB_EINVAL;
   }
@@ -261,6 +267,9 @@ int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const lo
   p.idofs = conv(idofs);
   p.nbPtrs = nb_ptrs;
   p.nbIdx = nb_idx;
+  if (n == 0) {
+    return 0;
+  }
   if (!p.dofs.present() || !p.neighInt.present() ||
       (nb_ptrs == nullptr && (nb_idx == nullptr || !p.idofs.present()))) {
     return SSB_EINVAL;

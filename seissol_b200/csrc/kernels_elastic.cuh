@@ -104,12 +104,14 @@ struct AderCtx {
   __device__ __forceinline__ void finish(int d, R (&out)[N]) {
     const R cd = static_cast<R>(p.coeffs[d]);
     R* icol = Ie + q * BP;
+    if (active) {  // padding threads alias (e=0,q=0): they must not repeat the read-modify-write
 #pragma unroll
-    for (int v = 0; v < N / 4; ++v) {
-      R t[4];
-      ld4(t, icol + 4 * v);
-      st4(icol + 4 * v, fma(cd, out[4 * v], t[0]), fma(cd, out[4 * v + 1], t[1]),
-          fma(cd, out[4 * v + 2], t[2]), fma(cd, out[4 * v + 3], t[3]));
+      for (int v = 0; v < N / 4; ++v) {
+        R t[4];
+        ld4(t, icol + 4 * v);
+        st4(icol + 4 * v, fma(cd, out[4 * v], t[0]), fma(cd, out[4 * v + 1], t[1]),
+            fma(cd, out[4 * v + 2], t[2]), fma(cd, out[4 * v + 3], t[3]));
+      }
     }
     if (d < O - 1 || wantDer) {
       // the bulk stores issued earlier must have finished reading the buffer we overwrite
@@ -227,9 +229,11 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
     // I = c0 * Q (own column)
     {
       const R c0 = static_cast<R>(p.coeffs[0]);
+      if (active) {
 #pragma unroll
-      for (int v = 0; v < BP / 4; ++v) {
-        st4(Ie + q * BP + 4 * v, c0 * acc[4 * v], c0 * acc[4 * v + 1], c0 * acc[4 * v + 2], c0 * acc[4 * v + 3]);
+        for (int v = 0; v < BP / 4; ++v) {
+          st4(Ie + q * BP + 4 * v, c0 * acc[4 * v], c0 * acc[4 * v + 1], c0 * acc[4 * v + 2], c0 * acc[4 * v + 3]);
+        }
       }
     }
     // dQ(0) = Q copy into the derivative family (Time.cpp:109-116)

@@ -161,9 +161,12 @@ def test_reference_layout_and_pointer_tables(gpu):
     ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=4, reference_layout=True)
     assert ctx.ld == 64 and ctx.der_ld[:3] == [64, 48, 32]
 
+    keep = []  # pointer tables are device tensors: keep them alive until the launches finish
+
     def table(t):
         stride = t.stride(0) * t.element_size()
-        return api.pointer_table(t.data_ptr() + stride * torch.arange(n, device=t.device, dtype=torch.int64))
+        keep.append(t.data_ptr() + stride * torch.arange(n, device=t.device, dtype=torch.int64))
+        return api.pointer_table(keep[-1])
 
     nb_ptrs = (data.buffers.data_ptr() + data.buffers.stride(0) * data.buffers.element_size()
                * data.neighbors).contiguous()
