@@ -9,13 +9,18 @@
 //             (src/Kernels/LinearCK/Neighbor.cpp:111-188: up to 4x48 launches).
 //   k_taylor: I = sum_d c_d dQ(d)  (Time::evaluateBatched, Time.cpp:257-292).
 //
-// Mapping (DESIGN.md §2): a CTA owns E elements; thread (e, q) owns quantity column q of
+// Mapping (DESIGN.md §3): a CTA owns E elements; thread (e, q) owns quantity column q of
 // element e in registers.  Element tensors live in shared memory as [e][q][k] with a
 // per-element stride padded so that 128-bit accesses of consecutive lanes (= consecutive
 // elements) are bank-conflict free; they arrive/leave by 1-D TMA bulk copies
 // (cp.async.bulk + mbarrier) straight from/to the per-element pointers of the batched
 // interface.  All constant operators are immediates in the instruction stream
 // (seissol_b200/codegen/gen_ops.py).
+//
+// The instruction stream of one thread is ~10^4 straight-line FFMAs (no reuse), so the
+// kernels are bound by instruction fetch unless >= 4 warps per SM sub-partition are
+// resident (tools/ubench/gen_ifetch.py): the shared-memory plan below is
+// squeezed to two regions per element (4 KB for order 6 / float) so that 16 warps fit.
 #pragma once
 #include "common.cuh"
 
@@ -63,24 +68,24 @@ struct TaylorParams {
 
 constexpr int kNQ = 9;
 __host__ __device__ constexpr int blockThreads(int E) { return (kNQ * E + 31) / 32 * 32; }
+__host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
 
-// Shared-memory plan of k_local, usable on host and device.
+// Shared-memory plan of k_local, usable on host and device.  Two regions per element:
+//   RQ : Q (TMA in) -> I (after the predictor) -> Q_new (TMA out)
+//   RD : dQ(odd) at +0, dQ(even>=2) at +offD2 during the predictor; afterwards the two
+//        face buffers F0/F1.  Without the predictor RD first receives Q.
 template <typename R, typename G, int E>
 struct LocalPlan {
   static constexpr int BP = G::kBP;
   static constexpr int B2P = G::kB2P;
-  static constexpr int SEQ = padOdd16(kNQ * BP, sizeof(R));                 // Q / I per element
-  static constexpr int D0LD = pad4i(G::derRows(1));
-  static constexpr int SED0 = padOdd16(kNQ * D0LD, sizeof(R));              // dQ(odd)
-  static constexpr int SEF = padOdd16(kNQ * B2P, sizeof(R));                // one face buffer
-  static constexpr int SELI = padOdd16(72 + 324, sizeof(R));                // star + nApNm1
-  static constexpr bool kFInQ = 2 * SEF <= SEQ;                             // F aliases the Q region
+  static constexpr int LD1 = pad4i(G::derRows(1));
+  static constexpr int LD2 = pad4i(G::derRows(2));
+  static constexpr int offD2 = kNQ * LD1;
+  static constexpr int SEQ = padOdd16(kNQ * BP, sizeof(R));
+  static constexpr int SED = padOdd16(imax(imax(kNQ * (LD1 + LD2), 2 * kNQ * B2P), kNQ * BP), sizeof(R));
   static constexpr int offQ = 0;
-  static constexpr int offI = offQ + E * SEQ;
-  static constexpr int offD0 = offI + E * SEQ;
-  static constexpr int offLI = offD0 + E * SED0;
-  static constexpr int offF = kFInQ ? offQ : offLI + E * SELI;
-  static constexpr int endReals = kFInQ ? offLI + E * SELI : offF + 2 * E * SEF;
+  static constexpr int offD = E * SEQ;
+  static constexpr int endReals = E * (SEQ + SED);
   static constexpr size_t barOffset = (size_t(endReals) * sizeof(R) + 15) / 16 * 16;
   static constexpr size_t bytes = barOffset + 16;
 };
@@ -95,29 +100,22 @@ struct AderCtx {
   static constexpr int O = G::kOrder;
   const LocalParams& p;
   R (&s)[3][3];
-  R* Qe; R* Ie; R* D0e; R* D1e; R* smem;
+  R (&icol)[BP];  // own column of the time-integrated DOFs, accumulated in registers
+  R* Qe; R* De;
   int r[3]; int q; int tid; bool active; bool wantDer; long long myElem;
-  __device__ __forceinline__ R* buf(int d) const { return d == 0 ? Qe : ((d & 1) ? D0e : D1e); }
+  __device__ __forceinline__ R* buf(int d) const { return d == 0 ? Qe : ((d & 1) ? De : De + P::offD2); }
   __device__ __forceinline__ static constexpr int ld(int d) { return d == 0 ? BP : pad4i(G::derRows(d)); }
   __device__ __forceinline__ const R* src(int d, int c) const { return buf(d - 1) + r[c] * ld(d - 1); }
-      template <int N>
+  template <int N>
   __device__ __forceinline__ void finish(int d, R (&out)[N]) {
     const R cd = static_cast<R>(p.coeffs[d]);
-    R* icol = Ie + q * BP;
-    if (active) {  // padding threads alias (e=0,q=0): they must not repeat the read-modify-write
 #pragma unroll
-      for (int v = 0; v < N / 4; ++v) {
-        R t[4];
-        ld4(t, icol + 4 * v);
-        st4(icol + 4 * v, fma(cd, out[4 * v], t[0]), fma(cd, out[4 * v + 1], t[1]),
-            fma(cd, out[4 * v + 2], t[2]), fma(cd, out[4 * v + 3], t[3]));
-      }
+    for (int k = 0; k < N; ++k) {
+      icol[k] = fma(cd, out[k], icol[k]);
     }
     if (d < O - 1 || wantDer) {
-      // the bulk stores issued earlier must have finished reading the buffer we overwrite
-      if (wantDer && tid < E) {
-        tma_store_wait_read();
-      }
+      // dQ(d) overwrites dQ(d-2), which everybody finished reading before the barrier of
+      // step d-1 (and whose bulk store, if any, was drained before that barrier too).
       R* dcol = buf(d) + q * N;
       if (active) {
 #pragma unroll
@@ -127,11 +125,14 @@ struct AderCtx {
       }
       if (wantDer) {
         fence_async_smem();
+        if (tid < E) {
+          tma_store_wait_read();  // store of dQ(d-1): its source is overwritten in step d+1
+        }
       }
       __syncthreads();
       if (wantDer && tid < E && myElem >= 0) {
         R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem))) + p.derOffset[d];
-        const R* srcb = ((d & 1) ? smem + P::offD0 + tid * P::SED0 : smem + P::offQ + tid * P::SEQ);
+        const R* srcb = De + ((d & 1) ? 0 : P::offD2);  // tid < E  =>  e == tid, De is this element's
         for (int c = 0; c < kNQ; ++c) {
           tma_store(dst + c * p.derLd[d], srcb + c * N, N * sizeof(R));
         }
@@ -143,9 +144,10 @@ struct AderCtx {
 
 // ---------------------------------------------------------------------------------------
 template <typename R, typename G, int E, bool ADER, bool LOCAL>
-__global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) {
+__global__ void __launch_bounds__(blockThreads(E), (blockThreads(E) <= 256 && sizeof(R) == 4) ? 2 : 1)
+    k_local(const LocalParams p) {
   using P = LocalPlan<R, G, E>;
-  constexpr int BP = P::BP, B2P = P::B2P, O = G::kOrder;
+  constexpr int BP = P::BP, B2P = P::B2P;
   extern __shared__ __align__(128) unsigned char smemRaw[];
   R* const smem = reinterpret_cast<R*>(smemRaw);
   uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::barOffset);
@@ -157,10 +159,7 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
   const long long slot = static_cast<long long>(blockIdx.x) * E;
 
   R* const Qe = smem + P::offQ + e * P::SEQ;
-  R* const Ie = smem + P::offI + e * P::SEQ;
-  R* const D0e = smem + P::offD0 + e * P::SED0;
-  R* const D1e = Qe;  // dQ(even >= 2) reuses the Q region (Q column is held in registers)
-  const R* const LIe = smem + P::offLI + e * P::SELI;
+  R* const De = smem + P::offD + e * P::SED;
 
   if (tid == 0) {
     mbar_init(bar, E);
@@ -168,26 +167,30 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
   }
   __syncthreads();
 
-  // ---- TMA loads: thread t < E fetches element slot+t
-  long long myElem = -1;
-  if (tid < E) {
-    const long long s = slot + tid;
-    if (s < p.n) {
-      myElem = p.perm != nullptr ? p.perm[s] : s;
+  // element of this thread's lane (el) -- for tid < E also the element this thread moves
+  long long el = -1;
+  {
+    const long long sl = slot + e;
+    if (sl < p.n) {
+      el = p.perm != nullptr ? p.perm[sl] : sl;
     }
-    uint32_t bytes = 0;
+  }
+  const long long myElem = tid < E ? el : -1;
+
+  // ---- TMA loads: thread t < E fetches element slot+t.  Predictor: Q -> RQ.
+  //      Without predictor: I -> RQ, Q -> RD.
+  if (tid < E) {
     if (myElem >= 0) {
       const uint32_t colBytes = BP * sizeof(R);
-      bytes = (72 + 324) * sizeof(R) + kNQ * colBytes * ((ADER ? 1 : 2));
-      mbar_arrive_expect_tx(bar, bytes);
-      R* const qDst = smem + P::offQ + tid * P::SEQ;
-      R* const iDst = smem + P::offI + tid * P::SEQ;
+      mbar_arrive_expect_tx(bar, kNQ * colBytes * (ADER ? 1 : 2));
+      R* const rq = smem + P::offQ + tid * P::SEQ;
+      R* const rd = smem + P::offD + tid * P::SED;
       const R* qSrc = static_cast<const R*>(p.dofs.at(myElem));
-      tma_load(smem + P::offLI + tid * P::SELI, p.localInt.at(myElem), (72 + 324) * sizeof(R), bar);
+      R* const qDst = ADER ? rq : rd;
       if (p.ldg == BP) {
         tma_load(qDst, qSrc, kNQ * colBytes, bar);
         if (!ADER) {
-          tma_load(iDst, p.idofs.at(myElem), kNQ * colBytes, bar);
+          tma_load(rq, p.idofs.at(myElem), kNQ * colBytes, bar);
         }
       } else {
         for (int c = 0; c < kNQ; ++c) {
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
         if (!ADER) {
           const R* iSrc = static_cast<const R*>(p.idofs.at(myElem));
           for (int c = 0; c < kNQ; ++c) {
-            tma_load(iDst + c * BP, iSrc + c * p.ldg, colBytes, bar);
+            tma_load(rq + c * BP, iSrc + c * p.ldg, colBytes, bar);
           }
         }
       }
@@ -204,39 +207,43 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
       mbar_arrive_expect_tx(bar, 0);
     }
   }
-  mbar_wait(bar, 0);
 
-  // ---- per-thread star coefficients of column q (3 source columns, zero padded)
+  // ---- per-thread star coefficients of column q (3 source columns, zero padded), read
+  //      straight from global memory while the bulk copies are in flight
+  const R* const LIg = el >= 0 ? static_cast<const R*>(p.localInt.at(el)) : nullptr;
   const int r0 = kStarRow[q][0], r1 = kStarRow[q][1], r2 = kStarRow[q][2];
   R s[3][3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    s[j][0] = LIe[24 * j + kStarOff[q] + 0];
-    s[j][1] = LIe[24 * j + kStarOff[q] + 1];
-    s[j][2] = kStarCnt[q] == 3 ? LIe[24 * j + kStarOff[q] + 2] : R(0);
+    s[j][0] = LIg != nullptr ? LIg[24 * j + kStarOff[q] + 0] : R(0);
+    s[j][1] = LIg != nullptr ? LIg[24 * j + kStarOff[q] + 1] : R(0);
+    s[j][2] = (LIg != nullptr && kStarCnt[q] == 3) ? LIg[24 * j + kStarOff[q] + 2] : R(0);
+  }
+  uint8_t ft[4] = {0, 0, 0, 0};
+  if (LOCAL && p.faceTypes != nullptr && el >= 0) {
+    const uchar4 t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
+    ft[0] = t.x; ft[1] = t.y; ft[2] = t.z; ft[3] = t.w;
   }
 
-  R acc[BP];  // own Q column
-#pragma unroll
-  for (int v = 0; v < BP / 4; ++v) {
-    R t[4];
-    ld4(t, Qe + q * BP + 4 * v);
-    acc[4 * v + 0] = t[0]; acc[4 * v + 1] = t[1]; acc[4 * v + 2] = t[2]; acc[4 * v + 3] = t[3];
-  }
+  mbar_wait(bar, 0);
+
+  R acc[BP];  // own Q column (LOCAL only)
 
   if constexpr (ADER) {
     const bool wantDer = p.derivs.present();
-    // I = c0 * Q (own column)
+    R icol[BP];
     {
       const R c0 = static_cast<R>(p.coeffs[0]);
-      if (active) {
 #pragma unroll
-        for (int v = 0; v < BP / 4; ++v) {
-          st4(Ie + q * BP + 4 * v, c0 * acc[4 * v], c0 * acc[4 * v + 1], c0 * acc[4 * v + 2], c0 * acc[4 * v + 3]);
-        }
+      for (int v = 0; v < BP / 4; ++v) {
+        R t[4];
+        ld4(t, Qe + q * BP + 4 * v);
+        icol[4 * v + 0] = c0 * t[0]; icol[4 * v + 1] = c0 * t[1];
+        icol[4 * v + 2] = c0 * t[2]; icol[4 * v + 3] = c0 * t[3];
       }
     }
-    // dQ(0) = Q copy into the derivative family (Time.cpp:109-116)
+    // dQ(0) = Q copy into the derivative family (Time.cpp:109-116); RQ stays intact
+    // until the predictor is complete.
     if (wantDer && tid < E && myElem >= 0) {
       R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem))) + p.derOffset[0];
       for (int c = 0; c < kNQ; ++c) {
@@ -245,19 +252,32 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
       tma_store_commit();
     }
 
-    // the dQ(0) bulk store reads the Q region, which step 2 overwrites: handled by the
-    // wait in finish(1) (executed before the barrier that precedes step 2's writes).
-    AderCtx<R, G, E> ctx{p, s, Qe, Ie, D0e, D1e, smem, {r0, r1, r2}, q, tid, active, wantDer, myElem};
+    AderCtx<R, G, E> ctx{p, s, icol, Qe, De, {r0, r1, r2}, q, tid, active, wantDer, myElem};
     G::template ader_run<R>(ctx);
 
+    if constexpr (LOCAL) {
+#pragma unroll
+      for (int v = 0; v < BP / 4; ++v) {
+        R t[4];
+        ld4(t, Qe + q * BP + 4 * v);
+        acc[4 * v + 0] = t[0]; acc[4 * v + 1] = t[1]; acc[4 * v + 2] = t[2]; acc[4 * v + 3] = t[3];
+      }
+    }
     if (wantDer && tid < E) {
-      tma_store_wait_read();
+      tma_store_wait_read();  // dQ(0) leaves RQ, the last dQ leaves RD
+    }
+    __syncthreads();  // everybody holds its Q column; nobody reads dQ any more
+    if (active) {
+#pragma unroll
+      for (int v = 0; v < BP / 4; ++v) {
+        st4(Qe + q * BP + 4 * v, icol[4 * v], icol[4 * v + 1], icol[4 * v + 2], icol[4 * v + 3]);
+      }
     }
     fence_async_smem();
-    __syncthreads();  // I complete and visible; D buffers free
+    __syncthreads();  // I complete and visible in RQ
     if (tid < E && myElem >= 0) {
       R* dst = static_cast<R*>(const_cast<void*>(p.idofs.at(myElem)));
-      const R* srcb = smem + P::offI + tid * P::SEQ;
+      const R* srcb = smem + P::offQ + tid * P::SEQ;
       if (p.ldg == BP) {
         tma_store(dst, srcb, kNQ * BP * sizeof(R));
       } else {
@@ -268,31 +288,33 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
       tma_store_commit();
     }
   } else {
-    if constexpr (P::kFInQ) {
-      __syncthreads();  // everyone has its Q column before F overwrites the Q region
+#pragma unroll
+    for (int v = 0; v < BP / 4; ++v) {
+      R t[4];
+      ld4(t, De + q * BP + 4 * v);
+      acc[4 * v + 0] = t[0]; acc[4 * v + 1] = t[1]; acc[4 * v + 2] = t[2]; acc[4 * v + 3] = t[3];
     }
+    __syncthreads();  // everybody holds its Q column before F overwrites RD
   }
 
   if constexpr (LOCAL) {
+    const R* const Ie = Qe;  // RQ now holds I
     // ---- volume: Q += sum_i kDivM_i . (I . star_i)
     G::template volume<R>(acc, Ie + r0 * BP, Ie + r1 * BP, Ie + r2 * BP, s);
 
     // ---- local flux: Q += rDivM_f . ((fMrT_f . I) . AplusT_f), skipped on DR faces
-    uint8_t ft[4] = {0, 0, 0, 0};
-    if (p.faceTypes != nullptr) {
-      const long long sl = slot + e;
-      if (sl < p.n) {
-        const long long el = p.perm != nullptr ? p.perm[sl] : sl;
-        const uchar4 t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
-        ft[0] = t.x; ft[1] = t.y; ft[2] = t.z; ft[3] = t.w;
-      }
-    }
-    R* const Fbase = smem + P::offF + e * P::SEF;
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
+      // column q of AplusT_f straight from global memory; latency hidden by fMrT
+      R a[kNQ];
+      const bool skip = ft[f] == 3 || LIg == nullptr;  // FaceType::DynamicRupture
+#pragma unroll
+      for (int c = 0; c < kNQ; ++c) {
+        a[c] = skip ? R(0) : LIg[72 + 81 * f + 9 * q + c];
+      }
       R F[B2P];
       G::template fMrT<R>(f, F, Ie + q * BP);
-      R* const Fe = Fbase + (f & 1) * E * P::SEF;
+      R* const Fe = De + (f & 1) * kNQ * B2P;
       if (active) {
 #pragma unroll
         for (int v = 0; v < B2P / 4; ++v) {
@@ -300,26 +322,28 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
         }
       }
       __syncthreads();
-      const bool skip = ft[f] == 3;  // FaceType::DynamicRupture
       R J[B2P];
 #pragma unroll
       for (int c = 0; c < kNQ; ++c) {
-        const R a = skip ? R(0) : LIe[72 + 81 * f + 9 * q + c];
 #pragma unroll
         for (int v = 0; v < B2P / 4; ++v) {
           R t[4];
           ld4(t, Fe + c * B2P + 4 * v);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            J[4 * v + i] = c == 0 ? a * t[i] : fma(a, t[i], J[4 * v + i]);
+            J[4 * v + i] = c == 0 ? a[c] * t[i] : fma(a[c], t[i], J[4 * v + i]);
           }
         }
       }
       G::template rDivM<R>(f, acc, J);
     }
 
-    // ---- write back Q
-    __syncthreads();  // all F reads done (F may alias the Q region)
+    // ---- write back Q through RQ (I has been read for the last time in fMrT_3; its bulk
+    //      store must have drained before the region is overwritten)
+    if (ADER && tid < E) {
+      tma_store_wait_read();
+    }
+    __syncthreads();
     if (active) {
 #pragma unroll
       for (int v = 0; v < BP / 4; ++v) {
@@ -347,29 +371,29 @@ __global__ void __launch_bounds__(blockThreads(E)) k_local(const LocalParams p) 
 }
 
 // ---------------------------------------------------------------------------------------
+// k_neigh shared-memory plan: one neighbor tile (TMA target, re-used for the own Q at the
+// end) and two face buffers per element.
 template <typename R, typename G, int E>
 struct NeighPlan {
   static constexpr int BP = G::kBP;
   static constexpr int B2P = G::kB2P;
   static constexpr int SEQ = padOdd16(kNQ * BP, sizeof(R));
-  static constexpr int SEF = padOdd16(kNQ * B2P, sizeof(R));
-  static constexpr int SENI = padOdd16(324, sizeof(R));
-  static constexpr int offA = 0;
-  static constexpr int offB = offA + E * SEQ;
-  static constexpr int offF = offB + E * SEQ;
-  static constexpr int offNI = offF + 2 * E * SEF;
-  static constexpr int endReals = offNI + E * SENI;
+  static constexpr int SEF = padOdd16(2 * kNQ * B2P, sizeof(R));
+  static constexpr int offN = 0;
+  static constexpr int offF = E * SEQ;
+  static constexpr int endReals = E * (SEQ + SEF);
   static constexpr size_t barOffset = (size_t(endReals) * sizeof(R) + 15) / 16 * 16;
-  static constexpr size_t bytes = barOffset + 32;
+  static constexpr size_t bytes = barOffset + 16;
 };
 
 template <typename R, typename G, int E>
-__global__ void __launch_bounds__(blockThreads(E)) k_neigh(const NeighParams p) {
+__global__ void __launch_bounds__(blockThreads(E), (blockThreads(E) <= 256 && sizeof(R) == 4) ? 2 : 1)
+    k_neigh(const NeighParams p) {
   using P = NeighPlan<R, G, E>;
   constexpr int BP = P::BP, B2P = P::B2P;
   extern __shared__ __align__(128) unsigned char smemRaw[];
   R* const smem = reinterpret_cast<R*>(smemRaw);
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smemRaw + P::barOffset);  // [0]=Q+NI, [1]=bufB, [2]=bufA
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::barOffset);
 
   const int tid = threadIdx.x;
   const bool active = tid < kNQ * E;
@@ -378,14 +402,11 @@ __global__ void __launch_bounds__(blockThreads(E)) k_neigh(const NeighParams p) 
   const long long slot = static_cast<long long>(blockIdx.x) * E;
 
   if (tid == 0) {
-    mbar_init(&bars[0], E);
-    mbar_init(&bars[1], E);
-    mbar_init(&bars[2], E);
+    mbar_init(bar, E);
     mbar_fence_init();
   }
   __syncthreads();
 
-  // element handled by this thread's lane (for face metadata) and by the loader thread
   long long el = -1;
   {
     const long long sl = slot + e;
@@ -407,25 +428,18 @@ __global__ void __launch_bounds__(blockThreads(E)) k_neigh(const NeighParams p) 
   } else {
     ft[0] = ft[1] = ft[2] = ft[3] = 255;
   }
+  const R* const NIg = el >= 0 ? static_cast<const R*>(p.neighInt.at(el)) : nullptr;
 
   const uint32_t colBytes = BP * sizeof(R);
-  // loader: neighbor tensor of face f of element slot+tid -> buffer
-  auto loadNeighbor = [&](int f, R* dstBase, uint64_t* bar) {
-    // called by threads tid < E only; here e == tid
-    const R* src = nullptr;
-    if (el >= 0 && ft[f] == 0) {
-      if (p.nbPtrs != nullptr) {
-        src = static_cast<const R*>(p.nbPtrs[4 * el + f]);
-      } else {
-        src = static_cast<const R*>(p.idofs.at(p.nbIdx[4 * el + f]));
-      }
-    }
+  R* const tile = smem + P::offN;
+  // loader (threads tid < E, e == tid): a [BP x 9] tensor -> this element's tile
+  auto loadTile = [&](const R* src) {
     if (src == nullptr) {
       mbar_arrive_expect_tx(bar, 0);
       return;
     }
     mbar_arrive_expect_tx(bar, kNQ * colBytes);
-    R* dst = dstBase + tid * P::SEQ;
+    R* dst = tile + tid * P::SEQ;
     if (p.ldg == BP) {
       tma_load(dst, src, kNQ * colBytes, bar);
     } else {
@@ -434,48 +448,36 @@ __global__ void __launch_bounds__(blockThreads(E)) k_neigh(const NeighParams p) 
       }
     }
   };
-
-  R* const bufA = smem + P::offA;
-  R* const bufB = smem + P::offB;
-  if (tid < E) {
-    if (el >= 0) {
-      mbar_arrive_expect_tx(&bars[0], kNQ * colBytes + 324 * sizeof(R));
-      const R* qSrc = static_cast<const R*>(p.dofs.at(el));
-      R* qDst = bufA + tid * P::SEQ;
-      if (p.ldg == BP) {
-        tma_load(qDst, qSrc, kNQ * colBytes, &bars[0]);
-      } else {
-        for (int c = 0; c < kNQ; ++c) {
-          tma_load(qDst + c * BP, qSrc + c * p.ldg, colBytes, &bars[0]);
-        }
-      }
-      tma_load(smem + P::offNI + tid * P::SENI, p.neighInt.at(el), 324 * sizeof(R), &bars[0]);
-    } else {
-      mbar_arrive_expect_tx(&bars[0], 0);
+  auto neighborOf = [&](int f) -> const R* {
+    if (el < 0 || ft[f] != 0) {
+      return nullptr;
     }
-    loadNeighbor(0, bufB, &bars[1]);
+    if (p.nbPtrs != nullptr) {
+      return static_cast<const R*>(p.nbPtrs[4 * el + f]);
+    }
+    return static_cast<const R*>(p.idofs.at(p.nbIdx[4 * el + f]));
+  };
+
+  if (tid < E) {
+    loadTile(neighborOf(0));
   }
 
-  mbar_wait(&bars[0], 0);
   R acc[BP];
 #pragma unroll
-  for (int v = 0; v < BP / 4; ++v) {
-    R t[4];
-    ld4(t, bufA + e * P::SEQ + q * BP + 4 * v);
-    acc[4 * v + 0] = t[0]; acc[4 * v + 1] = t[1]; acc[4 * v + 2] = t[2]; acc[4 * v + 3] = t[3];
-  }
-  __syncthreads();  // bufA free
-  if (tid < E) {
-    loadNeighbor(1, bufA, &bars[2]);
+  for (int k = 0; k < BP; ++k) {
+    acc[k] = R(0);
   }
 
-  const R* const NIe = smem + P::offNI + e * P::SENI;
 #pragma unroll
   for (int f = 0; f < 4; ++f) {
-    R* const buf = (f & 1) ? bufA : bufB;
-    uint64_t* const bar = (f & 1) ? &bars[2] : &bars[1];
-    mbar_wait(bar, (f >> 1) & 1);
     const bool regular = ft[f] == 0;
+    // column q of AminusT_f straight from global memory; latency hidden by rT/fP
+    R a[kNQ];
+#pragma unroll
+    for (int c = 0; c < kNQ; ++c) {
+      a[c] = regular ? NIg[81 * f + 9 * q + c] : R(0);
+    }
+    mbar_wait(bar, f & 1);
     R F[B2P];
     {
       R Gt[B2P];
@@ -485,50 +487,54 @@ __global__ void __launch_bounds__(blockThreads(E)) k_neigh(const NeighParams p) 
         F[i] = R(0);
       }
       if (regular) {
-        G::template rT<R>(fj[f], Gt, buf + e * P::SEQ + q * BP);
+        G::template rT<R>(fj[f], Gt, tile + e * P::SEQ + q * BP);
         G::template fP<R>(fh[f], F, Gt);
       }
     }
-    R* const Fe = smem + P::offF + (f & 1) * E * P::SEF + e * P::SEF;
+    R* const Fe = smem + P::offF + e * P::SEF + (f & 1) * kNQ * B2P;
     if (active) {
 #pragma unroll
       for (int v = 0; v < B2P / 4; ++v) {
         st4(Fe + q * B2P + 4 * v, F[4 * v], F[4 * v + 1], F[4 * v + 2], F[4 * v + 3]);
       }
     }
-    __syncthreads();  // F visible; `buf` no longer read
-    if (f + 2 < 4 && tid < E) {
-      loadNeighbor(f + 2, buf, bar);
+    __syncthreads();  // F visible; the tile is no longer read
+    if (tid < E) {
+      // next neighbor, or finally the element's own Q
+      loadTile(f < 3 ? neighborOf(f + 1) : (el >= 0 ? static_cast<const R*>(p.dofs.at(el)) : nullptr));
     }
     R J[B2P];
 #pragma unroll
     for (int c = 0; c < kNQ; ++c) {
-      const R a = regular ? NIe[81 * f + 9 * q + c] : R(0);
 #pragma unroll
       for (int v = 0; v < B2P / 4; ++v) {
         R t[4];
         ld4(t, Fe + c * B2P + 4 * v);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          J[4 * v + i] = c == 0 ? a * t[i] : fma(a, t[i], J[4 * v + i]);
+          J[4 * v + i] = c == 0 ? a[c] * t[i] : fma(a[c], t[i], J[4 * v + i]);
         }
       }
     }
     G::template rDivM<R>(f, acc, J);
   }
 
-  // write back through bufB (its last reader finished before the barrier of face 2)
+  // Q += acc: the own Q column arrived in the tile
+  mbar_wait(bar, 0);
   if (active) {
+    R* const qcol = tile + e * P::SEQ + q * BP;
 #pragma unroll
     for (int v = 0; v < BP / 4; ++v) {
-      st4(bufB + e * P::SEQ + q * BP + 4 * v, acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+      R t[4];
+      ld4(t, qcol + 4 * v);
+      st4(qcol + 4 * v, t[0] + acc[4 * v], t[1] + acc[4 * v + 1], t[2] + acc[4 * v + 2], t[3] + acc[4 * v + 3]);
     }
   }
   fence_async_smem();
   __syncthreads();
   if (tid < E && el >= 0) {
     R* dst = static_cast<R*>(const_cast<void*>(p.dofs.at(el)));
-    const R* srcb = bufB + tid * P::SEQ;
+    const R* srcb = tile + tid * P::SEQ;
     if (p.ldg == BP) {
       tma_store(dst, srcb, kNQ * colBytes);
     } else {
