@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""Benchmark of the ADER-DG element-update hot path (SeisSol proxy kernel `all`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the proxy kernel over the whole synthetic element batch
+(`proxy <cells> <steps> all`, src/Proxy/Runner.cpp:93-111).  Workload at every N: BASELINE.json
+configs[1], elastic ORDER=6 single precision, 1M elements PER GPU (weak scaling; the proxy's
+fake topology has no cross-GPU faces, so ranks are independent replicas -- DESIGN.md §7).
+Prints ONE JSON line (rank 0).  Metric: element-updates/s (cells x steps / time), the
+reference's own proxy metric (src/Proxy/Runner.cpp:122-144), plus non-zero GFLOP/s.
+
+`--impl reference` times the reference's own CPU implementation of the same path (the
+generated CPU kernels under oracle/_ref, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ORDER = 6
+REAL = 4
+KERNEL = "all"
+CELLS = 1_000_000
+CFG_NAME = {4: "elastic_o6_f32", 8: "elastic_o6_f64"}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_reference(real, budget_s, cells_hint=None):
+    """The reference's generated CPU kernels (oracle/_ref) on the host cores: proxy `all` on a
+    bounded sample.  Returns (elem-updates/s, cores, sample description, seconds, cells, steps)."""
+    from oracle import aderdg as O
+    from oracle import ref_lib
+    cfg = CFG_NAME[real]
+    if not ref_lib.available(cfg):
+        return None
+    R = ref_lib.RefLib(cfg)
+    dt = np.float32 if real == 4 else np.float64
+    coeffs = O.time_integrate_coeffs(ORDER, 0.0, 1.0, dt)
+    cores = R.threads()
+    # calibrate on a small batch, then size the sample for ~budget_s of CPU work
+    cal = O.proxy_data(ORDER, 256 * cores, dt, seed=3)
+    R.proxy(KERNEL, cal, coeffs, 1)
+    t, _, _ = R.proxy(KERNEL, cal, coeffs, 1)
+    rate = cal["Q"].shape[0] / max(t, 1e-9)
+    steps = 2
+    cells = int(max(1024, min(200_000, rate * budget_s / (steps + 1))))
+    if cells_hint:
+        cells = min(cells, cells_hint)
+    d = O.proxy_data(ORDER, cells, dt, seed=4)
+    R.proxy(KERNEL, d, coeffs, 1)                     # warm-up pass (Runner.cpp:93-95)
+    t, _, _ = R.proxy(KERNEL, d, coeffs, steps)
+    return cells * steps / t, cores, f"{cells} elements x {steps} passes of proxy `{KERNEL}`", t, cells, steps
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 alone times the CPU reference; other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from seissol_b200 import proxy
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    from oracle import aderdg as O
+    from oracle import ref_lib
+    cfg = CFG_NAME[args.real]
+    if not ref_lib.available(cfg):
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/libssref_{cfg}.so not built"}))
+        return 0
+    R = ref_lib.RefLib(cfg)
+    dt = np.float32 if args.real == 4 else np.float64
+    coeffs = O.time_integrate_coeffs(ORDER, 0.0, 1.0, dt)
+    cores = R.threads()
+    cal = O.proxy_data(ORDER, 256 * cores, dt, seed=3)
+    R.proxy(KERNEL, cal, coeffs, 1)
+    t, _, _ = R.proxy(KERNEL, cal, coeffs, 1)
+    rate = cal["Q"].shape[0] / max(t, 1e-9)
+    # whole run (warm-up + steps) bounded to ~2 minutes
+    cells = int(max(1024, min(args.cells, rate * 120.0 / (steps + warmup))))
+    d = O.proxy_data(ORDER, cells, dt, seed=4)
+    if warmup:
+        R.proxy(KERNEL, d, coeffs, warmup)
+    t, _, _ = R.proxy(KERNEL, d, coeffs, steps)
+    value = cells * steps / t
+    nz = proxy.nz_flops_per_element(ORDER, KERNEL)
+    sample = f"{cells} elements per step (bounded sample of the {args.cells}-element workload)"
+    line = {
+        "impl": "reference", "metric": "element-updates/s", "value": value, "unit": "element-updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.real == 4 else "f64", "data": "synthetic",
+        "gflops_nz": value * nz * 1e-9,
+        "config": {"workload": f"proxy elastic ORDER={ORDER} {'single' if args.real == 4 else 'double'} kernel={KERNEL}",
+                   "cells_per_gpu": args.cells, "sample_cells": cells},
+        "cpu_baseline": {"value": value, "unit": "element-updates/s", "cores": cores, "kind": "reference",
+                         "sample": sample,
+                         "note": "reference generated kernels, yateto generic C++ back-end (LIBXSMM/PSpaMM unavailable offline)"},
+        "e2e": {"value": value, "unit": "element-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from seissol_b200 import api, proxy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    ctx = api.Context(ORDER, args.real)
+    data = proxy.ProxyData.synthetic(ctx, args.cells, device, seed=42 + rank)
+    data.sort_by_face_relation()
+    k = proxy.ProxyKernels(ctx, data)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        k.all()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # events: [start, after k_local, after k_neigh] per step, all on the launching stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    for s in range(steps):
+        ev[s][0].record(stream)
+        k.local()
+        ev[s][1].record(stream)
+        k.neigh()
+        ev[s][2].record(stream)
+    t_end.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = t_begin.elapsed_time(t_end)
+    t_local = statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for s in range(steps))
+    t_neigh = statistics.mean(ev[s][1].elapsed_time(ev[s][2]) for s in range(steps))
+    finite = bool(torch.isfinite(data.dofs).all())
+    if world > 1:
+        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---- end to end: host buffers in, host buffers out, every step (pinned memory)
+    e2e_steps = max(1, min(steps, 5))
+    h_in = torch.empty(data.dofs.shape, dtype=data.dofs.dtype, pin_memory=True)
+    h_in.copy_(data.dofs)
+    h_out = torch.empty_like(h_in, pin_memory=True)
+    for _ in range(2):
+        data.dofs.copy_(h_in, non_blocking=True)
+        k.all()
+        h_out.copy_(data.dofs, non_blocking=True)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        data.dofs.copy_(h_in, non_blocking=True)
+        k.all()
+        h_out.copy_(data.dofs, non_blocking=True)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    io_bytes = data.dofs.numel() * data.dofs.element_size()
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        ms_per_step = total_ms / steps
+        value = world * args.cells / (ms_per_step * 1e-3)
+        nz = proxy.nz_flops_per_element(ORDER, KERNEL)
+        # dominant kernel = the longer of the two launches of a step
+        dom = "k_local" if t_local >= t_neigh else "k_neigh"
+        dom_ms = max(t_local, t_neigh)
+        dom_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, "local" if dom == "k_local" else "neigh")
+        achieved = dom_bytes * args.cells / (dom_ms * 1e-3) / 1e9
+        all_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, KERNEL)
+        line = {
+            "metric": "element-updates/s", "value": value, "unit": "element-updates/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.real == 4 else "f64", "data": "synthetic",
+            "gflops_nz": value * nz * 1e-9,
+            "config": {"workload": f"proxy elastic ORDER={ORDER} {'single' if args.real == 4 else 'double'} kernel={KERNEL}, "
+                                   f"{args.cells} elements per GPU (BASELINE.json configs[1])",
+                       "cells_per_gpu": args.cells, "l2": "inputs exceed L2 (%.1f GiB resident per GPU)" % (data.bytes_resident() / 2 ** 30),
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU", "finite": finite},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                         "ms_per_launch": dom_ms,
+                         "step": {"k_local_ms": t_local, "k_neigh_ms": t_neigh,
+                                  "all_algorithmic_GBs": all_bytes * args.cells / (ms_per_step * 1e-3) / 1e9,
+                                  "all_nz_tflops": args.cells / (ms_per_step * 1e-3) * nz * 1e-12}},
+            "e2e": {"value": world * args.cells * e2e_steps / (e2e_ms * 1e-3), "unit": "element-updates/s",
+                    "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps,
+                    "what": "per step: DOFs pinned host -> device, proxy `all` through the C ABI, DOFs device -> pinned host"},
+            "gpu_launches": 2 * steps,
+            "clocks": sampler.result(),
+        }
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_reference(args.real, 12.0)
+            if cpu is not None:
+                v, cores, sample, secs, _, _ = cpu
+                line["cpu_baseline"] = {"value": v, "unit": "element-updates/s", "cores": cores, "kind": "reference",
+                                        "sample": sample, "seconds": secs,
+                                        "note": "reference generated kernels, yateto generic C++ back-end "
+                                                "(LIBXSMM/PSpaMM unavailable offline), OpenMP over all host threads"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "element-updates/s", "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not built"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=CELLS)
+    ap.add_argument("--real", type=int, default=REAL, choices=[4, 8])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
