@@ -31,6 +31,7 @@ REAL = 4
 KERNEL = "all"
 CELLS = 1_000_000
 CFG_NAME = {4: "elastic_o6_f32", 8: "elastic_o6_f64"}
+FMA_PEAK = {4: 74.2, 8: 37.1}  # TFLOP/s, vector FMA, measured on this pool (tools/ubench/gen_ffma2.py); f64 = half rate
 
 
 def measured_peaks():
@@ -200,24 +201,27 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # events: [start, after k_local, after k_neigh] per step, all on the launching stream
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    # events: [start, after ader, after localwoader, after neigh] per step, all on the launching stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_begin.record(stream)
     for s in range(steps):
         ev[s][0].record(stream)
-        k.local()
+        k.ader()
         ev[s][1].record(stream)
-        k.neigh()
+        k.localwoader()
         ev[s][2].record(stream)
+        k.neigh()
+        ev[s][3].record(stream)
     t_end.record(stream)
     barrier()
     sampler.stop_flag.set()
     sampler.join()
     total_ms = t_begin.elapsed_time(t_end)
-    t_local = statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for s in range(steps))
-    t_neigh = statistics.mean(ev[s][1].elapsed_time(ev[s][2]) for s in range(steps))
+    t_ader = statistics.mean(ev[s][0].elapsed_time(ev[s][1]) for s in range(steps))
+    t_local = statistics.mean(ev[s][1].elapsed_time(ev[s][2]) for s in range(steps))
+    t_neigh = statistics.mean(ev[s][2].elapsed_time(ev[s][3]) for s in range(steps))
     finite = bool(torch.isfinite(data.dofs).all())
     if world > 1:
         t = torch.tensor([total_ms], device=device, dtype=torch.float64)
@@ -255,10 +259,13 @@ def run_ours(args):
         ms_per_step = total_ms / steps
         value = world * args.cells / (ms_per_step * 1e-3)
         nz = proxy.nz_flops_per_element(ORDER, KERNEL)
-        # dominant kernel = the longer of the two launches of a step
-        dom = "k_local" if t_local >= t_neigh else "k_neigh"
-        dom_ms = max(t_local, t_neigh)
-        dom_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, "local" if dom == "k_local" else "neigh")
+        # dominant kernel = the longest of the three launches of a step
+        names = {"k_local<ader>": (t_ader, "ader"), "k_local<localwoader>": (t_local, "localwoader"),
+                 "k_neigh": (t_neigh, "neigh")}
+        dom = max(names, key=lambda n: names[n][0])
+        dom_ms = names[dom][0]
+        dom_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, names[dom][1])
+        dom_flops = proxy.nz_flops_per_element(ORDER, names[dom][1])
         achieved = dom_bytes * args.cells / (dom_ms * 1e-3) / 1e9
         all_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, KERNEL)
         line = {
@@ -274,13 +281,16 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
                          "ms_per_launch": dom_ms,
-                         "step": {"k_local_ms": t_local, "k_neigh_ms": t_neigh,
+                         "fp32_fma": {"achieved_tflops": dom_flops * args.cells / (dom_ms * 1e-3) / 1e12,
+                                      "peak_tflops": FMA_PEAK[args.real], "frac": dom_flops * args.cells / (dom_ms * 1e-3) / 1e12 / FMA_PEAK[args.real],
+                                      "note": "non-zero flops of the dominant kernel vs the vector-FMA peak measured with tools/ubench (DESIGN.md §5)"},
+                         "step": {"k_ader_ms": t_ader, "k_localwoader_ms": t_local, "k_neigh_ms": t_neigh,
                                   "all_algorithmic_GBs": all_bytes * args.cells / (ms_per_step * 1e-3) / 1e9,
                                   "all_nz_tflops": args.cells / (ms_per_step * 1e-3) * nz * 1e-12}},
             "e2e": {"value": world * args.cells * e2e_steps / (e2e_ms * 1e-3), "unit": "element-updates/s",
                     "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps,
                     "what": "per step: DOFs pinned host -> device, proxy `all` through the C ABI, DOFs device -> pinned host"},
-            "gpu_launches": 2 * steps,
+            "gpu_launches": 3 * steps,
             "clocks": sampler.result(),
         }
         if world == 1 and not args.no_cpu:

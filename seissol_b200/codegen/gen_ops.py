@@ -58,9 +58,9 @@ def emit_acc(em, touched, name, k, coef, operand):
     """acc[k] (+)= coef*operand; first touch of a zero-initialised output is a plain mul."""
     if touched is not None and k not in touched:
         touched.add(k)
-        em.w(f"  {name}[{k}] = {lit(coef)} * {operand};")
+        em.w(f"  {name}[{k}] = pk_mulc({lit(coef)}, {operand});")
     else:
-        em.w(f"  {name}[{k}] = fma({lit(coef)}, {operand}, {name}[{k}]);")
+        em.w(f"  {name}[{k}] = pk_fmac({lit(coef)}, {operand}, {name}[{k}]);")
 
 
 def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
@@ -68,8 +68,9 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
     where a_c = column r_c of the source tensor (pointers a0,a1,a2 in shared memory).
     mats: list of 3 dense matrices (already restricted to [rows_out, rows_in])."""
     em.w("template <typename R>")
-    em.w(f"__device__ __forceinline__ void {fname}(R (&out)[{out_pad}], const R* __restrict__ a0,"
-         " const R* __restrict__ a1, const R* __restrict__ a2, const R (&s)[3][3]) {")
+    em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const R* __restrict__ a0,"
+         " const R* __restrict__ a1, const R* __restrict__ a2, const typename Pk<R>::T (&s)[3][3]) {")
+    em.w("  using P = typename Pk<R>::T; constexpr int V = Pk<R>::V;")
     touched = None if accumulate else set()
     nfma = 0
     for l0 in range(0, pad4(rows_in), 4):
@@ -78,14 +79,14 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
         if not cols:
             continue
         em.w("  {")
-        em.w(f"  R x0[4], x1[4], x2[4]; ld4(x0, a0 + {l0}); ld4(x1, a1 + {l0}); ld4(x2, a2 + {l0});")
+        em.w(f"  P x0[4], x1[4], x2[4]; ldv4(x0, a0 + {l0} * V); ldv4(x1, a1 + {l0} * V); ldv4(x2, a2 + {l0} * V);")
         for l in cols:
             for j, m in enumerate(mats):
                 ks = np.nonzero(m[:rows_out, l])[0]
                 if len(ks) == 0:
                     continue
                 i = l - l0
-                em.w(f"  {{ const R t = fma(s[{j}][2], x2[{i}], fma(s[{j}][1], x1[{i}], s[{j}][0] * x0[{i}]));")
+                em.w(f"  {{ const P t = pk_fma(s[{j}][2], x2[{i}], pk_fma(s[{j}][1], x1[{i}], pk_mul(s[{j}][0], x0[{i}])));")
                 nfma += 3
                 for k in ks:
                     emit_acc(em, touched, "out", int(k), m[k, l], "t")
@@ -95,7 +96,7 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
     if touched is not None:
         for k in range(out_pad):
             if k not in touched:
-                em.w(f"  out[{k}] = R(0);")
+                em.w(f"  out[{k}] = pk_zero<R>();")
     em.w("}")
     em.w()
     return nfma
@@ -104,15 +105,16 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
 def gen_spmv_smem(em, fname, m, out_pad, accumulate):
     """out (+)= M . x, x read from shared memory with 128-bit loads (column of length cols)."""
     rows, cols = m.shape
-    em.w("template <typename R>")
-    em.w(f"__device__ __forceinline__ void {fname}(R (&out)[{out_pad}], const R* __restrict__ x) {{")
+    em.w("template <typename R, typename Src>")
+    em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const Src& x) {{")
+    em.w("  using P = typename Pk<R>::T;")
     touched = None if accumulate else set()
     nfma = 0
     for l0 in range(0, pad4(cols), 4):
         ls = [l for l in range(l0, min(l0 + 4, cols)) if np.any(m[:, l] != 0)]
         if not ls:
             continue
-        em.w(f"  {{ R v[4]; ld4(v, x + {l0});")
+        em.w(f"  {{ P v[4]; x.load4(v, {l0});")
         for l in ls:
             for k in np.nonzero(m[:, l])[0]:
                 emit_acc(em, touched, "out", int(k), m[k, l], f"v[{l - l0}]")
@@ -121,7 +123,7 @@ def gen_spmv_smem(em, fname, m, out_pad, accumulate):
     if touched is not None:
         for k in range(out_pad):
             if k not in touched:
-                em.w(f"  out[{k}] = R(0);")
+                em.w(f"  out[{k}] = pk_zero<R>();")
     em.w("}")
     em.w()
     return nfma
@@ -130,7 +132,7 @@ def gen_spmv_smem(em, fname, m, out_pad, accumulate):
 def gen_spmv_reg(em, fname, m, in_pad, out_pad, accumulate):
     """out (+)= M . x with x in registers."""
     em.w("template <typename R>")
-    em.w(f"__device__ __forceinline__ void {fname}(R (&out)[{out_pad}], const R (&x)[{in_pad}]) {{")
+    em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const typename Pk<R>::T (&x)[{in_pad}]) {{")
     touched = None if accumulate else set()
     nfma = 0
     rows, cols = m.shape
@@ -141,14 +143,14 @@ def gen_spmv_reg(em, fname, m, in_pad, out_pad, accumulate):
     if touched is not None:
         for k in range(out_pad):
             if k not in touched:
-                em.w(f"  out[{k}] = R(0);")
+                em.w(f"  out[{k}] = pk_zero<R>();")
     em.w("}")
     em.w()
     return nfma
 
 
-def gen_dispatch(em, base, count, sig_decl, sig_call):
-    em.w("template <typename R>")
+def gen_dispatch(em, base, count, sig_decl, sig_call, src=False):
+    em.w("template <typename R, typename Src>" if src else "template <typename R>")
     em.w(f"__device__ __forceinline__ void {base}(int i, {sig_decl}) {{")
     em.w("  switch (i) {")
     for i in range(count):
@@ -192,16 +194,17 @@ def generate(order):
         stats[f"rDivM_{f}"] = gen_spmv_reg(em, f"rDivM_{f}", z["rDivM"][f], pad4(B2), pad4(B), True)
     for h in range(3):
         stats[f"fP_{h}"] = gen_spmv_reg(em, f"fP_{h}", z["fP"][h], pad4(B2), pad4(B2), False)
-    gen_dispatch(em, "fMrT", 4, f"R (&out)[{pad4(B2)}], const R* __restrict__ x", "out, x")
-    gen_dispatch(em, "rT", 4, f"R (&out)[{pad4(B2)}], const R* __restrict__ x", "out, x")
-    gen_dispatch(em, "rDivM", 4, f"R (&out)[{pad4(B)}], const R (&x)[{pad4(B2)}]", "out, x")
-    gen_dispatch(em, "fP", 3, f"R (&out)[{pad4(B2)}], const R (&x)[{pad4(B2)}]", "out, x")
+    PT = "typename Pk<R>::T"
+    gen_dispatch(em, "fMrT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src=True)
+    gen_dispatch(em, "rT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src=True)
+    gen_dispatch(em, "rDivM", 4, f"{PT} (&out)[{pad4(B)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
+    gen_dispatch(em, "fP", 3, f"{PT} (&out)[{pad4(B2)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
     # --- ADER driver: the kernel supplies a context with src()/finish() (hand-written)
     em.w("template <typename R, typename Ctx>")
     em.w("__device__ __forceinline__ void ader_run(Ctx& c) {")
     for d in range(1, order):
         n = pad4(nb3(order - d))
-        em.w(f"  {{ R out[{n}]; ader_step_{d}<R>(out, c.src({d}, 0), c.src({d}, 1), c.src({d}, 2), c.s);"
+        em.w(f"  {{ typename Pk<R>::T out[{n}]; ader_step_{d}<R>(out, c.src({d}, 0), c.src({d}, 1), c.src({d}, 2), c.s);"
              f" c.template finish<{n}>({d}, out); }}")
     em.w("}")
     em.w()

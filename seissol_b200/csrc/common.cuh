@@ -92,6 +92,116 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
   *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Packed lane type: a thread processes V elements at once.  float -> float2 driven by the
+// Blackwell packed-FP32 instructions (fma.rn.f32x2 -> SASS FFMA2; with a broadcast
+// compile-time constant ptxas emits the immediate form `FFMA2 R, R, imm, R`, i.e. two FMAs
+// per 16-byte instruction: half the instruction-fetch bytes per flop).
+// double -> plain double (V = 1).
+template <typename R> struct Pk;
+#ifndef SSB_PACK_F32
+#define SSB_PACK_F32 1  // 2: two elements per thread on packed FFMA2; 1: one element per thread, scalar FFMA
+#endif
+#if SSB_PACK_F32 == 2
+template <> struct Pk<float> { using T = float2; static constexpr int V = 2; };
+#else
+template <> struct Pk<float> { using T = float; static constexpr int V = 1; };
+#endif
+template <> struct Pk<double> { using T = double; static constexpr int V = 1; };
+
+__device__ __forceinline__ unsigned long long pk_bits(float2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ float2 pk_unbits(unsigned long long a) { return *reinterpret_cast<float2*>(&a); }
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_bits(a)), "l"(pk_bits(b)), "l"(pk_bits(c)));
+  return pk_unbits(d);
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_bits(a)), "l"(pk_bits(b)));
+  return pk_unbits(d);
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_bits(a)), "l"(pk_bits(b)));
+  return pk_unbits(d);
+}
+__device__ __forceinline__ float2 pk_fmac(float c, float2 x, float2 acc) { return pk_fma(make_float2(c, c), x, acc); }
+__device__ __forceinline__ float2 pk_mulc(float c, float2 x) { return pk_mul(make_float2(c, c), x); }
+__device__ __forceinline__ float pk_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float pk_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float pk_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float pk_fmac(float c, float x, float acc) { return fmaf(c, x, acc); }
+__device__ __forceinline__ float pk_mulc(float c, float x) { return c * x; }
+__device__ __forceinline__ float pk_get(float a, int) { return a; }
+__device__ __forceinline__ float pk_make(const float (&a)[1]) { return a[0]; }
+__device__ __forceinline__ float pk_sel01(float a, float) { return a; }
+__device__ __forceinline__ void ldv4(float (&v)[4], const float* p) { ld4(v, p); }
+__device__ __forceinline__ void stv4(float* p, float a, float b, float c, float d) { st4(p, a, b, c, d); }
+__device__ __forceinline__ void st4lane(float* p, int, float a, float b, float c, float d) { st4(p, a, b, c, d); }
+__device__ __forceinline__ double pk_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ double pk_mul(double a, double b) { return a * b; }
+__device__ __forceinline__ double pk_add(double a, double b) { return a + b; }
+__device__ __forceinline__ double pk_fmac(double c, double x, double acc) { return fma(c, x, acc); }
+__device__ __forceinline__ double pk_mulc(double c, double x) { return c * x; }
+template <typename R> __device__ __forceinline__ typename Pk<R>::T pk_zero();
+#if SSB_PACK_F32 == 2
+template <> __device__ __forceinline__ float2 pk_zero<float>() { return make_float2(0.f, 0.f); }
+#else
+template <> __device__ __forceinline__ float pk_zero<float>() { return 0.f; }
+#endif
+template <> __device__ __forceinline__ double pk_zero<double>() { return 0.0; }
+// lane v of a packed value / packed value from per-lane scalars
+__device__ __forceinline__ float pk_get(float2 a, int v) { return v == 0 ? a.x : a.y; }
+__device__ __forceinline__ double pk_get(double a, int) { return a; }
+__device__ __forceinline__ float2 pk_make(const float (&a)[2]) { return make_float2(a[0], a[1]); }
+__device__ __forceinline__ double pk_make(const double (&a)[1]) { return a[0]; }
+// keep lane 0 of a, lane 1 of b
+__device__ __forceinline__ float2 pk_sel01(float2 a, float2 b) { return make_float2(a.x, b.y); }
+__device__ __forceinline__ double pk_sel01(double a, double) { return a; }
+
+// 4 consecutive packed entries from a lane-interleaved column ([k][V] reals)
+__device__ __forceinline__ void ldv4(float2 (&v)[4], const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+  v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void ldv4(double (&v)[4], const double* p) { ld4(v, p); }
+__device__ __forceinline__ void stv4(float* p, float2 a, float2 b, float2 c, float2 d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ void stv4(double* p, double a, double b, double c, double d) { st4(p, a, b, c, d); }
+
+// Operand sources of the generated sparse mat-vec code: a lane-interleaved column, or V
+// separate per-element columns (TMA landing zones) packed on the fly.
+template <typename R> struct SrcPk {
+  const R* p;
+  __device__ __forceinline__ void load4(typename Pk<R>::T (&v)[4], int k0) const { ldv4(v, p + k0 * Pk<R>::V); }
+};
+template <typename R> struct SrcSplit;
+template <> struct SrcSplit<float> {
+  const float* p0; const float* p1;
+  __device__ __forceinline__ void load4(float2 (&v)[4], int k0) const {
+    const float4 a = *reinterpret_cast<const float4*>(p0 + k0);
+    const float4 b = *reinterpret_cast<const float4*>(p1 + k0);
+    v[0] = make_float2(a.x, b.x); v[1] = make_float2(a.y, b.y);
+    v[2] = make_float2(a.z, b.z); v[3] = make_float2(a.w, b.w);
+  }
+  __device__ __forceinline__ void load4(float (&v)[4], int k0) const { ld4(v, p0 + k0); }
+};
+template <> struct SrcSplit<double> {
+  const double* p0; const double* p1;
+  __device__ __forceinline__ void load4(double (&v)[4], int k0) const { ld4(v, p0 + k0); }
+};
+// lane v of 4 packed values -> one 128-bit (float) / 256-bit (double) store
+__device__ __forceinline__ void st4lane(float* p, int v, float2 a, float2 b, float2 c, float2 d) {
+  st4(p, pk_get(a, v), pk_get(b, v), pk_get(c, v), pk_get(d, v));
+}
+__device__ __forceinline__ void st4lane(double* p, int, double a, double b, double c, double d) { st4(p, a, b, c, d); }
+
 // pad a per-element shared-memory stride (in reals) so that stride*sizeof/16 is odd:
 // 128-bit accesses of 8 consecutive lanes (one element each) then hit 8 distinct
 // 16-byte bank groups -> conflict-free.

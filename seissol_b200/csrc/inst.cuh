@@ -7,8 +7,27 @@
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
 #define SSB_GEN SSB_CAT(gen_o, SSB_ORDER)
 
+#include <cstdlib>
+
 namespace ssb {
 namespace {
+
+// grid size: one CTA per batch, or (SSB_PERSISTENT=k) k CTAs per SM walking the batches in lock step
+inline unsigned gridFor(long long batches) {
+  static int persistent = -1;
+  static int sms = 0;
+  if (persistent < 0) {
+    const char* e = std::getenv("SSB_PERSISTENT");
+    persistent = e != nullptr ? std::atoi(e) : 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (persistent > 0 && batches > static_cast<long long>(persistent) * sms) {
+    return static_cast<unsigned>(persistent * sms);
+  }
+  return static_cast<unsigned>(batches);
+}
 
 // Traits binding the generated operator code of one order to the kernel templates.
 struct Gen {
@@ -23,27 +42,32 @@ struct Gen {
   template <typename R, typename Ctx>
   __device__ __forceinline__ static void ader_run(Ctx& c) { SSB_GEN::ader_run<R>(c); }
   template <typename R>
-  __device__ __forceinline__ static void volume(R (&acc)[kBP], const R* a0, const R* a1, const R* a2,
-                                                const R (&s)[3][3]) {
+  __device__ __forceinline__ static void volume(typename Pk<R>::T (&acc)[kBP], const R* a0, const R* a1, const R* a2,
+                                                const typename Pk<R>::T (&s)[3][3]) {
     SSB_GEN::volume<R>(acc, a0, a1, a2, s);
   }
+  template <typename R, typename Src>
+  __device__ __forceinline__ static void fMrT(int f, typename Pk<R>::T (&out)[kB2P], const Src& x) {
+    SSB_GEN::fMrT<R>(f, out, x);
+  }
+  template <typename R, typename Src>
+  __device__ __forceinline__ static void rT(int f, typename Pk<R>::T (&out)[kB2P], const Src& x) {
+    SSB_GEN::rT<R>(f, out, x);
+  }
   template <typename R>
-  __device__ __forceinline__ static void fMrT(int f, R (&out)[kB2P], const R* x) { SSB_GEN::fMrT<R>(f, out, x); }
-  template <typename R>
-  __device__ __forceinline__ static void rT(int f, R (&out)[kB2P], const R* x) { SSB_GEN::rT<R>(f, out, x); }
-  template <typename R>
-  __device__ __forceinline__ static void rDivM(int f, R (&out)[kBP], const R (&x)[kB2P]) {
+  __device__ __forceinline__ static void rDivM(int f, typename Pk<R>::T (&out)[kBP], const typename Pk<R>::T (&x)[kB2P]) {
     SSB_GEN::rDivM<R>(f, out, x);
   }
   template <typename R>
-  __device__ __forceinline__ static void fP(int h, R (&out)[kB2P], const R (&x)[kB2P]) {
+  __device__ __forceinline__ static void fP(int h, typename Pk<R>::T (&out)[kB2P], const typename Pk<R>::T (&x)[kB2P]) {
     SSB_GEN::fP<R>(h, out, x);
   }
 };
 
 using Real = SSB_REAL;
-constexpr int EL = SSB_E_LOCAL;
+constexpr int EL = SSB_E_LOCAL;  // groups of V elements per CTA
 constexpr int EN = SSB_E_NEIGH;
+constexpr int VL = Pk<Real>::V;
 
 template <bool ADER, bool LOCAL>
 int launchLocal(const LocalParams& p, cudaStream_t stream) {
@@ -60,7 +84,7 @@ int launchLocal(const LocalParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
-  const unsigned grid = unsigned((p.n + EL - 1) / EL);
+  const unsigned grid = gridFor((p.n + EL * VL - 1) / (EL * VL));
   kern<<<grid, blockThreads(EL), P::bytes, stream>>>(p);
   return int(cudaGetLastError());
 }
@@ -89,7 +113,7 @@ int neighEntry(const NeighParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
-  const unsigned grid = unsigned((p.n + EN - 1) / EN);
+  const unsigned grid = gridFor((p.n + EN * VL - 1) / (EN * VL));
   kern<<<grid, blockThreads(EN), P::bytes, stream>>>(p);
   return int(cudaGetLastError());
 }
@@ -107,7 +131,7 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
-const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL, EN, localEntry, neighEntry, taylorEntry};
+const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry};
 
 }  // namespace
 

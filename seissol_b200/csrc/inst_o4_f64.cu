@@ -4,9 +4,9 @@
 #define SSB_REAL double
 #define SSB_TAG o4_f64
 #ifndef SSB_E_LOCAL
-#define SSB_E_LOCAL 28
+#define SSB_E_LOCAL 14
 #endif
 #ifndef SSB_E_NEIGH
-#define SSB_E_NEIGH 28
+#define SSB_E_NEIGH 14
 #endif
 #include "inst.cuh"

@@ -126,14 +126,21 @@ class ProxyData:
         x = t.detach().cpu().numpy().reshape(t.shape[0], 9, self.ctx.ld)
         return np.ascontiguousarray(x[:, :, :self.ctx.B].transpose(0, 2, 1))
 
-    def sort_by_face_relation(self):
-        """Processing order that makes the neighbor's face id j uniform per CTA for all four
-        faces (256 classes), removing warp divergence in the rT_j selection of k_neigh.
+    def sort_by_face_relation(self, coarse=False):
+        """Processing order that makes (neighbor's face id j, orientation h) of all four faces
+        uniform inside a warp and inside the element pairs that share packed FFMA2
+        instructions (12^4 classes), removing divergence in the rT_j / fP_h selection of k_neigh.
         This is our analogue of the reference's recorder grouping by ConditionalKey
         (src/Initializer/BatchRecorders/NeighIntegrationRecorder.cpp:142-144)."""
         t = self.torch
         j = self.face_rel[:, :, 0].to(t.int64)
-        key = j[:, 0] + 4 * j[:, 1] + 16 * j[:, 2] + 64 * j[:, 3]
+        h = self.face_rel[:, :, 1].to(t.int64)
+        # j (selects the large rT operators) varies slowest: all CTAs resident at one time execute
+        # the same instruction stream, which the instruction caches reward (DESIGN.md §4);
+        # h (small fP operators) is sorted inside a j class.
+        key = (j[:, 0] + 4 * j[:, 1] + 16 * j[:, 2] + 64 * j[:, 3]) * 81
+        if not coarse:
+            key = key + h[:, 0] + 3 * h[:, 1] + 9 * h[:, 2] + 27 * h[:, 3]
         self.perm = t.argsort(key, stable=True).to(t.int32).contiguous()
         return self.perm
 
@@ -160,10 +167,18 @@ class ProxyKernels:
         self.ctx.local(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.local_int),
                        d.face_types, d.cells, stream=stream)
 
-    def local(self, stream=None):
+    def local(self, stream=None, fused=False):
+        """ader ∘ localwoader.  Two launches by default: the fused kernel (`ssb_ader_local`, I never
+        leaves the SM) executes 12k straight-line instructions per thread and is instruction-fetch
+        bound; the two smaller kernels run 35 % faster although I makes a round trip through L2/HBM
+        (profiles/)."""
         d = self.d
-        self.ctx.ader_local(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
-                            d.face_types, self.coeffs, d.cells, stream=stream)
+        if fused:
+            self.ctx.ader_local(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
+                                d.face_types, self.coeffs, d.cells, stream=stream)
+        else:
+            self.ader(stream)
+            self.localwoader(stream)
 
     def neigh(self, stream=None):
         d = self.d
@@ -179,7 +194,7 @@ class ProxyKernels:
             getattr(self, part)(stream)
 
     def launches(self, name):
-        return sum({"all": 2, "local": 1, "neigh": 1, "ader": 1, "localwoader": 1}[p] for p in name.split(","))
+        return sum({"all": 3, "local": 2, "neigh": 1, "ader": 1, "localwoader": 1}[p] for p in name.split(","))
 
 
 def run_proxy(order, real_size, cells, timesteps, kernel, device="cuda:0", data=None, sort=True):

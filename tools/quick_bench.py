@@ -19,11 +19,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--kernels", default="ader,localwoader,local,neigh,all")
     ap.add_argument("--nosort", action="store_true")
+    ap.add_argument("--coarse", action="store_true")
     a = ap.parse_args()
     ctx = api.Context(a.order, a.real)
     d = proxy.ProxyData.synthetic(ctx, a.cells)
     if not a.nosort:
-        d.sort_by_face_relation()
+        d.sort_by_face_relation(coarse=a.coarse)
     k = proxy.ProxyKernels(ctx, d)
     print(f"order {a.order} real {a.real} cells {a.cells} E_local {ctx.e_local} E_neigh {ctx.e_neigh} "
           f"resident {d.bytes_resident() / 2**30:.2f} GiB")
