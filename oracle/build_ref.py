@@ -73,21 +73,24 @@ def compile_cfg(ref, cfg, force=False):
     lib = libpath(cfg)
     harness = os.path.join(HERE, "ref_harness_visco.cpp" if eq == "viscoelastic2" else "ref_harness.cpp")
     if (not force and os.path.exists(lib)
-            and os.path.getmtime(lib) > os.path.getmtime(harness)):
+            and os.path.getmtime(lib) > max(os.path.getmtime(harness),
+                                            os.path.getmtime(os.path.join(HERE, "ref_rs.cpp")))):
         return lib
     sub = generate(ref, cfg)
     objs = []
-    flags = ["-std=c++17", "-O2", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-w", "-fno-gnu-unique", "-fvisibility-inlines-hidden",
+    flags = ["-std=c++17", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-w", "-fno-gnu-unique", "-fvisibility-inlines-hidden",
              f"-I{sub}", f"-I{os.path.join(ref, 'submodules', 'yateto', 'include')}",
              f"-DSSREF_ORDER={order}"] + (["-DSSREF_DOUBLE"] if prec == "d" else []) \
         + ([f"-DSSREF_MECHANISMS={mech}"] if mech else [])
     procs = []
     t0 = time.time()
+    rs_flags = [f"-I{os.path.join(HERE, 'stub')}", f"-I{os.path.join(ref, 'src')}"]
     for src in [os.path.join(sub, "kernel.cpp"), os.path.join(sub, "init.cpp"),
-                os.path.join(sub, "tensor.cpp"), harness]:
+                os.path.join(sub, "tensor.cpp"), harness, os.path.join(HERE, "ref_rs.cpp")]:
         obj = os.path.join(REFDIR, "gen", cfg, os.path.basename(src) + ".o")
         objs.append(obj)
-        procs.append(subprocess.Popen(["g++", *flags, "-c", src, "-o", obj]))
+        extra = rs_flags if src.endswith("ref_rs.cpp") else []
+        procs.append(subprocess.Popen(["g++", *flags, *extra, "-c", src, "-o", obj]))
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"compile failed for {cfg}")

@@ -1,0 +1,121 @@
+"""CPU tests of the friction oracle (oracle/friction.py): the rate-and-state helper functions are pinned
+against the reference header compiled verbatim into oracle/_ref; pre-/post-compute against the closed
+forms the reference's own unit tests use (tests/DynamicRupture/FrictionLaws/FrictionSolverCommon.t.h
+style: Uphoff thesis eq. 4.53/4.60); the composed laws are checked for physical invariants."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import aderdg as O
+from oracle import friction as F
+from oracle import ref_lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("cfg,dt", [("elastic_o6_f32", np.float32), ("elastic_o6_f64", np.float64)])
+def test_rs_helpers_match_reference_header(cfg, dt):
+    if not ref_lib.available(cfg):
+        pytest.skip("oracle/_ref not built here")
+    lib = ref_lib.RefLib(cfg).lib
+    lib.ssref_rs_almost_zero.restype = ctypes.c_double
+    assert float(F.almost_zero(dt)) == pytest.approx(lib.ssref_rs_almost_zero(), rel=1e-6)
+    rng = np.random.default_rng(0)
+    n = 4000
+    x = (10.0 ** rng.uniform(-30, 6, n) * rng.choice([-1, 1], n)).astype(dt)
+    c = rng.uniform(-80, 80, n).astype(dt)
+    e = F.compute_c_exp(c)
+    e_ref = np.zeros_like(c)
+    lib.ssref_rs_cexp(ctypes.c_int64(n), _p(c), _p(e_ref))
+    tol = 20 * np.finfo(dt).eps
+    assert np.allclose(e, e_ref, rtol=tol, atol=0)
+    out, dout = np.zeros_like(x), np.zeros_like(x)
+    lib.ssref_rs_arsinhexp(ctypes.c_int64(n), _p(x), _p(c), _p(e_ref), _p(out), _p(dout))
+    # the large-exponent branch computes c + log(...): rounding is relative to |c|, not to the result
+    assert np.all(np.abs(F.arsinhexp(x, c, e_ref) - out) <= tol * np.maximum(np.abs(out), np.abs(c)) + np.finfo(dt).tiny)
+    assert np.allclose(F.arsinhexp_derivative(x, c, e_ref), dout, rtol=tol, atol=np.finfo(dt).tiny)
+    xs = (10.0 ** rng.uniform(-6, 12, n)).astype(dt)
+    cs = rng.uniform(0.5, 90, n).astype(dt)
+    ls = np.zeros_like(xs)
+    lib.ssref_rs_logsinh(ctypes.c_int64(n), _p(xs), _p(cs), _p(ls))
+    assert np.allclose(F.logsinh(xs, cs), ls, rtol=tol, atol=tol)
+    # identity the helpers exist for: asinh(x e^c) where it does not overflow
+    m = np.abs(c) < 20
+    direct = np.arcsinh(x[m].astype(np.float64) * np.exp(c[m].astype(np.float64)))
+    big = np.abs(direct) > 1e-3   # tiny results underflow in single precision
+    assert np.all(np.abs(out[m][big] - direct[big]) <= 50 * np.finfo(dt).eps * np.maximum(np.abs(direct[big]), np.abs(c[m][big])))
+
+
+def test_resample_matrix_orientation():
+    cfg = "elastic_o6_f64"
+    if not ref_lib.available(cfg):
+        pytest.skip("oracle/_ref not built here")
+    R = ref_lib.RefLib(cfg)
+    tab = O.load_tables(6, np.float64)
+    x = np.random.default_rng(1).uniform(-1, 1, (5, 49))
+    assert np.allclose(R.resample(x), x @ tab["resample"].T, rtol=1e-13, atol=1e-14)
+    # resampling reproduces constants (partition of unity of the nodal basis)
+    assert np.allclose(tab["resample"] @ np.ones(49), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_pre_and_postcompute_closed_forms(dt):
+    order, nf = 4, 3
+    P = (order + 1) ** 2
+    st, imp, _ = F.fault_state("lsw", nf, order, dt)
+    qip, qim = F.fault_qinterpolated(nf, order, dt)
+    f = 1
+    ns, t1, t2 = F.precompute_stress(imp, f, qip[f], qim[f], 1.0)
+    # eq. 4.53: theta = eta * (v- - v+ + sigma+/Z+ + sigma-/Z-), in float64 from the definitions
+    q64p, q64m = qip[f].astype(np.float64), qim[f].astype(np.float64)
+    zp, zpn = float(imp["zp"][f]), float(imp["zpNeig"][f])
+    want = (zp * zpn / (zp + zpn)) * (q64m[..., 6] - q64p[..., 6] + q64p[..., 0] / zp + q64m[..., 0] / zpn)
+    assert np.allclose(ns, want, rtol=50 * np.finfo(dt).eps, atol=1e-3 if dt == np.float32 else 1e-9)
+    # identical states on both sides and matched impedances: no jump -> theta = sigma, and with the
+    # tractions returned unchanged the imposed state equals the time average of the input state
+    imp2 = F.impedances(2670.0, np.full(nf, 6000.0), np.full(nf, 3464.0), 2670.0, np.full(nf, 6000.0), np.full(nf, 3464.0), dt)
+    ns, t1, t2 = F.precompute_stress(imp2, f, qip[f], qip[f], 1.0)
+    assert np.allclose(ns, qip[f][..., 0], rtol=1e-5) and np.allclose(t1, qip[f][..., 3], rtol=1e-5)
+    w = np.full(order, 1.0 / order)
+    plus, minus = F.postcompute_imposed(imp2, f, ns, t1, t2, qip[f], qip[f], w)
+    mean = qip[f].astype(np.float64).mean(axis=0)
+    for q in (0, 3, 5, 6, 7, 8):
+        assert np.allclose(plus[:, q], mean[:, q], rtol=1e-4, atol=1e-4 * np.abs(mean[:, q]).max())
+        assert np.allclose(minus[:, q], mean[:, q], rtol=1e-4, atol=1e-4 * np.abs(mean[:, q]).max())
+    assert np.all(plus[:, [1, 2, 4]] == 0)
+    assert P == plus.shape[0]
+
+
+@pytest.mark.parametrize("law_name", ["lsw", "rsfvw"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_laws_run_and_respect_invariants(law_name, dt):
+    order, nf = 4, 6
+    tab = O.load_tables(order, dt)
+    st, imp, params = F.fault_state(law_name, nf, order, dt)
+    qip, qim = F.fault_qinterpolated(nf, order, dt)
+    law = (F.LinearSlipWeakening if law_name == "lsw" else F.RateAndStateFastVelocityWeakening)(params, tab["resample"])
+    pts, wts = O.gauss_legendre_shifted(order, 0.0, 1e-3)
+    dts = F.delta_t(pts)
+    assert np.isclose(dts.sum(), 1e-3)
+    before = {k: v.copy() for k, v in st.items()}
+    plus, minus = F.evaluate(law, st, imp, qip, qim, 0.0, dts, wts / 1e-3)
+    for k, v in st.items():
+        assert np.all(np.isfinite(v.astype(np.float64))), k
+    assert np.all(np.isfinite(plus)) and np.all(np.isfinite(minus))
+    # tractions are continuous across the fault, slip rate is non-negative, slip accumulates
+    assert np.array_equal(plus[..., [0, 3, 5]], minus[..., [0, 3, 5]])
+    assert np.all(st["slipRateMagnitude"] >= 0)
+    assert np.all(st["peakSlipRate"] >= st["slipRateMagnitude"] - 1e-30)
+    assert np.all(np.abs(st["accumulatedSlipMagnitude"]) >= np.abs(before["accumulatedSlipMagnitude"]) - 1e-12)
+    if law_name == "lsw":
+        assert np.all((st["mu"] <= st["muS"] + 1e-6) & (st["mu"] >= st["muD"] - 1e-6))
+        # the forced-rupture patch is fully weakened
+        assert np.allclose(st["mu"][:, : (order + 1) ** 2 // 4], st["muD"][:, : (order + 1) ** 2 // 4])
+    else:
+        if dt == np.float64:
+            # single precision cannot meet the reference's default |g| < 1e-8 on a slipping fault
+            assert st["convergenceInner"].all() and st["convergenceOuter"].all()
+        assert np.all(st["mu"] > 0) and np.all(st["mu"] < 1.5)
