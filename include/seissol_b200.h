@@ -52,7 +52,8 @@ void ssb_destroy(ssb_ctx* ctx);
 int ssb_set_layout(ssb_ctx* ctx, int ld_q, const int* der_offset, const int* der_ld);
 int ssb_layout_reference(ssb_ctx* ctx);
 /* out[0]=#basis functions B, [1]=ld_q, [2]=Q size (reals), [3]=derivative family size,
- * [4..4+O) = der_offset, [12..12+O) = der_ld, [20] = elements per CTA (local), [21] = (neigh) */
+ * [4..4+O) = der_offset, [12..12+O) = der_ld, [20] = elements per CTA (local), [21] = (neigh),
+ * [22] = fault points P, [23] = ppad */
 int ssb_query(const ssb_ctx* ctx, int* out24);
 
 /* ader: Cauchy-Kovalevskaya predictor.  Replaces Spacetime::computeBatchedAder
@@ -93,6 +94,71 @@ int ssb_taylor(ssb_ctx* ctx, ssb_array_t derivs, ssb_array_t idofs, const double
 int ssb_neigh(ssb_ctx* ctx, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
               ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types,
               const uint8_t* face_rel, long long n, const int* perm, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dynamic rupture.  Fault tensors use the reference's layout: point index fastest, padded to
+ * `ppad` points (default: multiple of 4; ssb_layout_reference: 64-byte aligned like
+ * dr::misc::NumPaddedPoints, src/DynamicRupture/Misc.h:63-66):
+ * QInterpolated{Plus,Minus}[face][O][9][ppad], ImposedState{Plus,Minus}[face][9][ppad],
+ * every per-point array [face][ppad], bool arrays as uint8 [face][ppad]. */
+int ssb_set_dr_layout(ssb_ctx* ctx, int ppad);
+
+/* godunov_dr: space-time interpolation at the fault.  Replaces
+ * kernels::DynamicRupture::batchedSpaceTimeInterpolation (src/Kernels/DynamicRupture.cpp:110-168).
+ * der_plus/der_minus: per FACE the derivative family of the plus / minus element
+ * (DynamicRupture::TimeDerivative{Plus,Minus}Device); tinv_t: device [n][81] (DRGodunovData::dataTinvT);
+ * face_info: device uint8 [n][3] = DRFaceInformation{plusSide, minusSide, faceRelation};
+ * coeffs: HOST [O][O], row s = point-evaluation coefficients tau_s^d/d! of time point s
+ * (src/Numerical/TimeBasis.h:71-80 at the Gauss-Legendre points, DynamicRupture.cpp:62-70). */
+int ssb_dr_interp(ssb_ctx* ctx, ssb_array_t der_plus, ssb_array_t der_minus, const void* tinv_t,
+                  const uint8_t* face_info, void* q_plus, void* q_minus, const double* coeffs,
+                  long long n_faces, const int* perm, void* stream);
+
+/* FrictionLawData as a structure of DEVICE arrays (src/Memory/Descriptor/DynamicRupture.h:47-265). */
+typedef struct ssb_friction_data {
+  const void* q_plus; const void* q_minus;            /* QInterpolatedPlus/Minus */
+  void* imposed_plus; void* imposed_minus;            /* ImposedStatePlus/Minus [n][9][ppad] */
+  const void* imp_and_eta;                            /* [n][11] ImpedancesAndEta (DynamicRupture/Typedefs.h:23-35) */
+  const void* initial_stress;                         /* InitialStressInFaultCS [n][6][ppad] */
+  void* mu; void* slip1; void* slip2; void* slip_rate1; void* slip_rate2; void* slip_rate_magnitude;
+  void* accumulated_slip_magnitude; void* traction1; void* traction2; void* rupture_time;
+  void* peak_slip_rate; void* dyn_stress_time;
+  uint8_t* rupture_time_pending; uint8_t* dyn_stress_time_pending;
+  const void* d_c; const void* mu_s; const void* mu_d; const void* cohesion; const void* forced_rupture_time; /* LSW */
+  const void* rs_a; const void* rs_sl0; const void* rs_f0; const void* rs_mu_w; const void* rs_b; const void* rs_sr_w;
+  void* state_variable; uint8_t* convergence_inner; uint8_t* convergence_outer;                      /* RS */
+  const void* resample_t;                             /* [P][P], resample_t[j*P+p] = init::resample[p][j] */
+} ssb_friction_data_t;
+
+/* Scalars of FrictionSolver::evaluate and FrictionLawParameters (DynamicRupture/Misc.h:254-287). */
+typedef struct ssb_friction_params {
+  double delta_t[8];       /* FrictionSolver::computeDeltaT (FrictionSolver.cpp:20-37) */
+  double time_weights[8];
+  double full_update_time;
+  double eta_p_damp;       /* drParameters.etaDamp while etaDampEnd > fullUpdateTime, else 1 */
+  double healing_threshold;
+  double t0;
+  double rs_sr0;
+  double rs_slip_rate_tolerance;
+  double rs_state_tolerance;
+  int rs_max_number_slip_rate_updates;
+  int rs_number_state_variable_updates;
+} ssb_friction_params_t;
+
+/* FrictionSolver::evaluate (src/DynamicRupture/FrictionLaws/FrictionSolver.h:41) for
+ * LinearSlipWeakeningLaw<NoSpecialization> and RateAndStateBase<FastVelocityWeakeningLaw<NoTP>>;
+ * one thread per fault quadrature point, convergence decided per face like the CPU implementation. */
+int ssb_friction_lsw(ssb_ctx* ctx, const ssb_friction_data_t* data, const ssb_friction_params_t* params,
+                     long long n_faces, void* stream);
+int ssb_friction_rsfvw(ssb_ctx* ctx, const ssb_friction_data_t* data, const ssb_friction_params_t* params,
+                       long long n_faces, void* stream);
+
+/* neigh_dr: nodal flux of the imposed state into the adjacent elements.  Replaces the DynamicRupture
+ * branch of Neighbor::computeBatchedNeighborsIntegral (src/Kernels/LinearCK/Neighbor.cpp:150-186).
+ * godunov / flux_solver: device [n][4] pointer tables (CellDRMapping, src/Initializer/Typedefs.h:265-270),
+ * NULL entries for non-DR faces; side_rel: device uint8 [n][4][2] = {side, faceRelation}. */
+int ssb_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, const void* const* godunov, const void* const* flux_solver,
+                 const uint8_t* side_rel, const uint8_t* face_types, long long n, void* stream);
 
 const char* ssb_error_string(int code);
 const char* ssb_version(void);

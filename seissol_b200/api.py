@@ -15,12 +15,37 @@ LIB_PATH = os.path.join(HERE, "lib", "libseissol_b200.so")
 SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",
     "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_neigh",
+    "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_error_string", "ssb_version",
 ]
 
 
 class SsbArray(ctypes.Structure):
     _fields_ = [("ptrs", ctypes.c_void_p), ("base", ctypes.c_void_p), ("stride_bytes", ctypes.c_longlong)]
+
+
+FRICTION_DATA_FIELDS = [
+    "q_plus", "q_minus", "imposed_plus", "imposed_minus", "imp_and_eta", "initial_stress",
+    "mu", "slip1", "slip2", "slip_rate1", "slip_rate2", "slip_rate_magnitude", "accumulated_slip_magnitude",
+    "traction1", "traction2", "rupture_time", "peak_slip_rate", "dyn_stress_time",
+    "rupture_time_pending", "dyn_stress_time_pending",
+    "d_c", "mu_s", "mu_d", "cohesion", "forced_rupture_time",
+    "rs_a", "rs_sl0", "rs_f0", "rs_mu_w", "rs_b", "rs_sr_w", "state_variable", "convergence_inner",
+    "convergence_outer", "resample_t"]
+
+
+class SsbFrictionData(ctypes.Structure):
+    """ssb_friction_data_t: FrictionLawData as device pointers."""
+    _fields_ = [(name, ctypes.c_void_p) for name in FRICTION_DATA_FIELDS]
+
+
+class SsbFrictionParams(ctypes.Structure):
+    """ssb_friction_params_t."""
+    _fields_ = [("delta_t", ctypes.c_double * 8), ("time_weights", ctypes.c_double * 8),
+                ("full_update_time", ctypes.c_double), ("eta_p_damp", ctypes.c_double),
+                ("healing_threshold", ctypes.c_double), ("t0", ctypes.c_double), ("rs_sr0", ctypes.c_double),
+                ("rs_slip_rate_tolerance", ctypes.c_double), ("rs_state_tolerance", ctypes.c_double),
+                ("rs_max_number_slip_rate_updates", ctypes.c_int), ("rs_number_state_variable_updates", ctypes.c_int)]
 
 
 class SsbError(RuntimeError):
@@ -52,6 +77,11 @@ def load_library():
     lib.ssb_ader_local.argtypes = [P, A, A, A, A, P, P, LL, P, P]
     lib.ssb_taylor.argtypes = [P, A, A, P, LL, P]
     lib.ssb_neigh.argtypes = [P, A, P, P, A, A, P, P, LL, P, P]
+    lib.ssb_set_dr_layout.argtypes = [P, I]
+    lib.ssb_dr_interp.argtypes = [P, A, A, P, P, P, P, P, LL, P, P]
+    lib.ssb_friction_lsw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
+    lib.ssb_friction_rsfvw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
+    lib.ssb_neigh_dr.argtypes = [P, A, P, P, P, P, LL, P]
     _lib = lib
     return lib
 
@@ -107,6 +137,7 @@ class Context:
         self.der_offset = [out[4 + d] for d in range(self.order)]
         self.der_ld = [out[12 + d] for d in range(self.order)]
         self.e_local, self.e_neigh = out[20], out[21]
+        self.P, self.ppad = out[22], out[23]
 
     def __del__(self):
         try:
@@ -142,3 +173,23 @@ class Context:
               perm=None, stream=None):
         _check(self.lib.ssb_neigh(self.handle, dofs, _ptr(nb_ptrs), _ptr(nb_idx), idofs, neigh_int,
                                   _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
+
+    # -- dynamic rupture ------------------------------------------------------------------------
+    def dr_interp(self, der_plus, der_minus, tinv_t, face_info, q_plus, q_minus, coeffs, n, perm=None, stream=None):
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        assert c.shape == (self.order, self.order)
+        _check(self.lib.ssb_dr_interp(self.handle, der_plus, der_minus, _ptr(tinv_t), _ptr(face_info), _ptr(q_plus),
+                                      _ptr(q_minus), c.ctypes.data_as(ctypes.c_void_p), n, _ptr(perm), _stream(stream)))
+
+    def friction(self, law, data, params, n, stream=None):
+        """law: 'lsw' | 'rsfvw'; data: dict name -> torch tensor (FRICTION_DATA_FIELDS); params: SsbFrictionParams."""
+        d = SsbFrictionData()
+        for name in FRICTION_DATA_FIELDS:
+            t = data.get(name)
+            setattr(d, name, None if t is None else t.data_ptr())
+        fn = self.lib.ssb_friction_lsw if law == "lsw" else self.lib.ssb_friction_rsfvw
+        _check(fn(self.handle, ctypes.byref(d), ctypes.byref(params), n, _stream(stream)))
+
+    def neigh_dr(self, dofs, godunov_ptrs, flux_solver_ptrs, side_rel, face_types, n, stream=None):
+        _check(self.lib.ssb_neigh_dr(self.handle, dofs, _ptr(godunov_ptrs), _ptr(flux_solver_ptrs), _ptr(side_rel),
+                                     _ptr(face_types), n, _stream(stream)))

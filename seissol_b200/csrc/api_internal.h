@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels_elastic.cuh"
+#include "kernels_dr.cuh"
 
 namespace ssb {
 
@@ -19,6 +20,23 @@ struct KernelSet {
   int (*neigh)(const NeighParams&, cudaStream_t);
   int (*taylor)(const TaylorParams&, cudaStream_t);
 };
+
+struct DrKernelSet {
+  int order;
+  int realSize;
+  int P;    // fault quadrature points
+  int PP;   // padded to 4
+  int (*interp)(DrInterpParams&, cudaStream_t);
+  int (*friction)(const FrictionParams&, int law, cudaStream_t);
+  int (*neighDr)(const NeighDrParams&, cudaStream_t);
+};
+
+const DrKernelSet* drkernelset_o4_f32();
+const DrKernelSet* drkernelset_o5_f32();
+const DrKernelSet* drkernelset_o6_f32();
+const DrKernelSet* drkernelset_o4_f64();
+const DrKernelSet* drkernelset_o5_f64();
+const DrKernelSet* drkernelset_o6_f64();
 
 const KernelSet* kernelset_o4_f32();
 const KernelSet* kernelset_o5_f32();

@@ -11,6 +11,8 @@ using namespace ssb;
 
 struct ssb_ctx {
   const KernelSet* ks;
+  const DrKernelSet* dr;
+  int ppad;
   int order;
   int realSize;
   int equation;
@@ -56,6 +58,26 @@ ElemArray conv(const ssb_array_t& a) {
   r.base = static_cast<const char*>(a.base);
   r.strideBytes = a.stride_bytes;
   return r;
+}
+
+const DrKernelSet* lookupDr(int order, int realSize) {
+  if (realSize == 4) {
+    switch (order) {
+      case 4: return drkernelset_o4_f32();
+      case 5: return drkernelset_o5_f32();
+      case 6: return drkernelset_o6_f32();
+      default: return nullptr;
+    }
+  }
+  if (realSize == 8) {
+    switch (order) {
+      case 4: return drkernelset_o4_f64();
+      case 5: return drkernelset_o5_f64();
+      case 6: return drkernelset_o6_f64();
+      default: return nullptr;
+    }
+  }
+  return nullptr;
 }
 
 const KernelSet* lookup(int order, int realSize) {
@@ -133,6 +155,8 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
     return SSB_EINVAL;
   }
   c->ks = ks;
+  c->dr = lookupDr(order, real_size);
+  c->ppad = c->dr != nullptr ? c->dr->PP : 0;
   c->order = order;
   c->realSize = real_size;
   c->equation = equation;
@@ -168,6 +192,10 @@ int ssb_layout_reference(ssb_ctx* c) {
     return SSB_EINVAL;
   }
   referenceLayout(c);
+  if (c->dr != nullptr) {
+    const int per = 64 / c->realSize;
+    c->ppad = (c->dr->P + per - 1) / per * per;
+  }
   return 0;
 }
 
@@ -186,6 +214,8 @@ int ssb_query(const ssb_ctx* c, int* out) {
   }
   out[20] = c->ks->eLocal;
   out[21] = c->ks->eNeigh;
+  out[22] = c->dr != nullptr ? c->dr->P : 0;
+  out[23] = c->ppad;
   return 0;
 }
 
@@ -280,6 +310,143 @@ int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const lo
   p.n = n;
   p.ldg = c->ldq;
   return c->ks->neigh(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_set_dr_layout(ssb_ctx* c, int ppad) {
+  if (c == nullptr || c->dr == nullptr || ppad < c->dr->PP || ppad % 4 != 0) {
+    return SSB_EINVAL;
+  }
+  c->ppad = ppad;
+  return 0;
+}
+
+int ssb_dr_interp(ssb_ctx* c, ssb_array_t der_plus, ssb_array_t der_minus, const void* tinv_t,
+                  const uint8_t* face_info, void* q_plus, void* q_minus, const double* coeffs, long long n,
+                  const int* perm, void* stream) {
+  if (c == nullptr || c->dr == nullptr || n < 0 || coeffs == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  DrInterpParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.derPlus = conv(der_plus);
+  p.derMinus = conv(der_minus);
+  if (!p.derPlus.present() || !p.derMinus.present() || tinv_t == nullptr || face_info == nullptr ||
+      q_plus == nullptr || q_minus == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.tinvT = tinv_t;
+  p.faceInfo = face_info;
+  p.qPlus = q_plus;
+  p.qMinus = q_minus;
+  p.perm = perm;
+  p.n = n;
+  p.ppad = c->ppad;
+  p.derSize = c->derSize;
+  for (int d = 0; d < c->order; ++d) {
+    p.derOffset[d] = c->derOffset[d];
+    p.derLd[d] = c->derLd[d];
+    for (int s = 0; s < c->order; ++s) {
+      p.coeffs[s][d] = coeffs[s * c->order + d];
+    }
+  }
+  return c->dr->interp(p, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int friction(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params_t* q, long long n, int law,
+             void* stream) {
+  if (c == nullptr || c->dr == nullptr || n < 0 || d == nullptr || q == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  FrictionParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.qPlus = d->q_plus; p.qMinus = d->q_minus; p.imposedPlus = d->imposed_plus; p.imposedMinus = d->imposed_minus;
+  p.impAndEta = d->imp_and_eta; p.initialStress = d->initial_stress;
+  p.mu = d->mu; p.slip1 = d->slip1; p.slip2 = d->slip2; p.slipRate1 = d->slip_rate1; p.slipRate2 = d->slip_rate2;
+  p.slipRateMagnitude = d->slip_rate_magnitude; p.accumulatedSlipMagnitude = d->accumulated_slip_magnitude;
+  p.traction1 = d->traction1; p.traction2 = d->traction2; p.ruptureTime = d->rupture_time;
+  p.peakSlipRate = d->peak_slip_rate; p.dynStressTime = d->dyn_stress_time;
+  p.ruptureTimePending = d->rupture_time_pending; p.dynStressTimePending = d->dyn_stress_time_pending;
+  p.dC = d->d_c; p.muS = d->mu_s; p.muD = d->mu_d; p.cohesion = d->cohesion; p.forcedRuptureTime = d->forced_rupture_time;
+  p.rsA = d->rs_a; p.rsSl0 = d->rs_sl0; p.rsF0 = d->rs_f0; p.rsMuW = d->rs_mu_w; p.rsB = d->rs_b; p.rsSrW = d->rs_sr_w;
+  p.stateVariable = d->state_variable; p.convergenceInner = d->convergence_inner; p.convergenceOuter = d->convergence_outer;
+  p.resampleT = d->resample_t;
+  const void* common[] = {p.qPlus, p.qMinus, p.imposedPlus, p.imposedMinus, p.impAndEta, p.initialStress, p.mu,
+                          p.slip1, p.slip2, p.slipRate1, p.slipRate2, p.slipRateMagnitude, p.accumulatedSlipMagnitude,
+                          p.traction1, p.traction2, p.ruptureTime, p.peakSlipRate, p.dynStressTime,
+                          p.ruptureTimePending, p.dynStressTimePending, p.resampleT};
+  for (const void* x : common) {
+    if (x == nullptr) {
+      return SSB_EINVAL;
+    }
+  }
+  if (law == 0) {
+    if (p.dC == nullptr || p.muS == nullptr || p.muD == nullptr || p.cohesion == nullptr || p.forcedRuptureTime == nullptr) {
+      return SSB_EINVAL;
+    }
+  } else {
+    if (p.rsA == nullptr || p.rsSl0 == nullptr || p.rsF0 == nullptr || p.rsMuW == nullptr || p.rsB == nullptr ||
+        p.rsSrW == nullptr || p.stateVariable == nullptr || p.convergenceInner == nullptr || p.convergenceOuter == nullptr) {
+      return SSB_EINVAL;
+    }
+  }
+  p.n = n;
+  p.ppad = c->ppad;
+  for (int i = 0; i < 8; ++i) {
+    p.deltaT[i] = q->delta_t[i];
+    p.timeWeights[i] = q->time_weights[i];
+  }
+  p.fullUpdateTime = q->full_update_time;
+  p.etaPDamp = q->eta_p_damp;
+  p.healingThreshold = q->healing_threshold;
+  p.t0 = q->t0;
+  p.rsSr0 = q->rs_sr0;
+  p.rsSlipRateTolerance = q->rs_slip_rate_tolerance;
+  p.rsStateTolerance = q->rs_state_tolerance;
+  p.rsMaxNumberSlipRateUpdates = q->rs_max_number_slip_rate_updates;
+  p.rsNumberStateVariableUpdates = q->rs_number_state_variable_updates;
+  return c->dr->friction(p, law, static_cast<cudaStream_t>(stream));
+}
+}  // namespace
+
+int ssb_friction_lsw(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params_t* q, long long n,
+                     void* stream) {
+  return friction(c, d, q, n, 0, stream);
+}
+
+int ssb_friction_rsfvw(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params_t* q, long long n,
+                       void* stream) {
+  return friction(c, d, q, n, 1, stream);
+}
+
+int ssb_neigh_dr(ssb_ctx* c, ssb_array_t dofs, const void* const* godunov, const void* const* flux_solver,
+                 const uint8_t* side_rel, const uint8_t* face_types, long long n, void* stream) {
+  if (c == nullptr || c->dr == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  NeighDrParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  if (!p.dofs.present() || godunov == nullptr || flux_solver == nullptr || side_rel == nullptr || face_types == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.godunov = godunov;
+  p.fluxSolver = flux_solver;
+  p.sideRel = side_rel;
+  p.faceTypes = face_types;
+  p.n = n;
+  p.ldg = c->ldq;
+  p.ppad = c->ppad;
+  return c->dr->neighDr(p, static_cast<cudaStream_t>(stream));
 }
 
 const char* ssb_error_string(int code) {

@@ -202,6 +202,32 @@ __device__ __forceinline__ void st4lane(float* p, int v, float2 a, float2 b, flo
 }
 __device__ __forceinline__ void st4lane(double* p, int, double a, double b, double c, double d) { st4(p, a, b, c, d); }
 
+
+// scalar type of a packed lane type, zero of a packed lane type, scalar broadcast
+template <typename PT> struct PkScalar;
+template <> struct PkScalar<float2> { using T = float; static constexpr int V = 2; };
+template <> struct PkScalar<float> { using T = float; static constexpr int V = 1; };
+template <> struct PkScalar<double> { using T = double; static constexpr int V = 1; };
+template <typename PT> __device__ __forceinline__ PT pk_zero_of();
+template <> __device__ __forceinline__ float2 pk_zero_of<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float pk_zero_of<float>() { return 0.f; }
+template <> __device__ __forceinline__ double pk_zero_of<double>() { return 0.0; }
+template <typename PT> __device__ __forceinline__ PT pk_bcast(typename PkScalar<PT>::T x);
+template <> __device__ __forceinline__ float2 pk_bcast<float2>(float x) { return make_float2(x, x); }
+template <> __device__ __forceinline__ float pk_bcast<float>(float x) { return x; }
+template <> __device__ __forceinline__ double pk_bcast<double>(double x) { return x; }
+// Dynamic-rupture kernels always pack two TIME POINTS per thread in single precision.
+template <typename R> struct PkDr;
+template <> struct PkDr<float> { using T = float2; static constexpr int V = 2; };
+template <> struct PkDr<double> { using T = double; static constexpr int V = 1; };
+// operand source: a register-resident column
+template <typename PT, int N> struct SrcReg {
+  const PT (&x)[N];
+  __device__ __forceinline__ void load4(PT (&v)[4], int k0) const {
+    v[0] = x[k0]; v[1] = x[k0 + 1]; v[2] = x[k0 + 2]; v[3] = x[k0 + 3];
+  }
+};
+
 // pad a per-element shared-memory stride (in reals) so that stride*sizeof/16 is odd:
 // 128-bit accesses of 8 consecutive lanes (one element each) then hit 8 distinct
 // 16-byte bank groups -> conflict-free.

@@ -221,3 +221,139 @@ def run_proxy(order, real_size, cells, timesteps, kernel, device="cuda:0", data=
         "gflops-nz": nz * 1e-9 / dt, "gibs": by / 2 ** 30 / dt,
         "elem-updates-per-s": cells * timesteps / dt,
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# Dynamic rupture (proxy kernels godunov_dr, neigh_dr, all_dr; src/Proxy/Allocator.cpp:193-294)
+def gauss_legendre_points(order, dt):
+    """Gauss-Legendre points/weights on [0, dt] (src/Numerical/Quadrature.h:76-90)."""
+    x, w = np.polynomial.legendre.leggauss(order)
+    return 0.5 * dt * (x + 1.0), 0.5 * dt * w
+
+
+def point_coeffs(order, tau):
+    """MonomialBasis::point (src/Numerical/TimeBasis.h:71-80): tau^d / d!."""
+    return np.array([tau ** d / math.factorial(d) for d in range(order)])
+
+
+def ders_to_device(ctx, ders, np_dtype):
+    """list over d of [n, B, 9] -> [n, dersize] in the context's derivative-family layout."""
+    n = ders[0].shape[0]
+    out = np.zeros((n, ctx.dersize), dtype=np_dtype)
+    for d, dq in enumerate(ders):
+        rows = nbasis(ctx.order - d)
+        blk = np.zeros((n, 9, ctx.der_ld[d]), dtype=np_dtype)
+        blk[:, :, :rows] = dq[:, :rows, :].transpose(0, 2, 1)
+        out[:, ctx.der_offset[d]:ctx.der_offset[d] + 9 * ctx.der_ld[d]] = blk.reshape(n, -1)
+    return out
+
+
+def points_to_device(ctx, x):
+    """[..., P, 9] -> [..., 9, ppad] (point index fastest, zero padding)."""
+    out = np.zeros(x.shape[:-2] + (9, ctx.ppad), dtype=x.dtype)
+    out[..., :x.shape[-2]] = np.swapaxes(x, -1, -2)
+    return out
+
+
+def points_from_device(ctx, x, P):
+    """[..., 9, ppad] -> [..., P, 9]."""
+    return np.ascontiguousarray(np.swapaxes(x[..., :P], -1, -2))
+
+
+def friction_params(order, dt, full_update_time=0.0, **kw):
+    """ssb_friction_params_t for one time step: Gauss-Legendre sub-steps (FrictionSolver.cpp:20-37) and
+    time weights normalised by dt as TimeCluster::computeDynamicRupture does."""
+    pts, wts = gauss_legendre_points(order, dt)
+    delta = np.empty(order)
+    delta[0] = pts[0]
+    delta[1:] = np.diff(pts)
+    delta[-1] += pts[0]
+    p = api.SsbFrictionParams()
+    for i in range(order):
+        p.delta_t[i] = delta[i]
+        p.time_weights[i] = wts[i] / dt
+    p.full_update_time = full_update_time
+    p.eta_p_damp = kw.get("eta_p_damp", 1.0)
+    p.healing_threshold = kw.get("healing_threshold", -1.0)
+    p.t0 = kw.get("t0", 0.0)
+    p.rs_sr0 = kw.get("rs_sr0", 1e-6)
+    p.rs_slip_rate_tolerance = kw.get("rs_slip_rate_tolerance", 1e-8)
+    p.rs_state_tolerance = kw.get("rs_state_tolerance", 1e-8)
+    p.rs_max_number_slip_rate_updates = kw.get("rs_max_number_slip_rate_updates", 60)
+    p.rs_number_state_variable_updates = kw.get("rs_number_state_variable_updates", 10)
+    return p, delta, wts / dt
+
+
+class DrProxyData:
+    """Fault-side fake data of the proxy: 4 fault faces per cell, each picking random plus/minus cells'
+    derivative families; every cell face maps to a random fault face (src/Proxy/Allocator.cpp:230-294)."""
+
+    def __init__(self, ctx, data, seed=7, scale=1e-2):
+        import torch
+        t = torch
+        self.ctx, self.data = ctx, data
+        dev, dt = data.device, data.dtype
+        cells = data.cells
+        self.faces = 4 * cells
+        g = t.Generator(device=dev)
+        g.manual_seed(seed)
+        self.derivs = t.rand((cells, ctx.dersize), generator=g, device=dev, dtype=dt)
+        self.plus_cell = t.randint(0, cells, (self.faces,), generator=g, device=dev, dtype=t.int64)
+        self.minus_cell = t.randint(0, cells, (self.faces,), generator=g, device=dev, dtype=t.int64)
+        info = t.empty((self.faces, 3), dtype=t.uint8, device=dev)
+        info[:, 0] = t.randint(0, 4, (self.faces,), generator=g, device=dev).to(t.uint8)
+        info[:, 1] = t.randint(0, 4, (self.faces,), generator=g, device=dev).to(t.uint8)
+        info[:, 2] = t.randint(0, 3, (self.faces,), generator=g, device=dev).to(t.uint8)
+        self.face_info = info.contiguous()
+        self.tinv_t = (t.rand((self.faces, 81), generator=g, device=dev, dtype=dt) * 2 - 1).contiguous()
+        self.q_plus = t.zeros((self.faces, ctx.order, 9, ctx.ppad), device=dev, dtype=dt)
+        self.q_minus = t.zeros_like(self.q_plus)
+        self.imposed_plus = ((t.rand((self.faces, 9, ctx.ppad), generator=g, device=dev, dtype=dt) * 2 - 1) * scale)
+        self.flux_solver = ((t.rand((self.faces, 81), generator=g, device=dev, dtype=dt) * 2 - 1)).contiguous()
+        # CellDRMapping per (cell, face)
+        sr = t.empty((cells, 4, 2), dtype=t.uint8, device=dev)
+        sr[:, :, 0] = t.randint(0, 4, (cells, 4), generator=g, device=dev).to(t.uint8)
+        sr[:, :, 1] = t.randint(0, 3, (cells, 4), generator=g, device=dev).to(t.uint8)
+        self.side_rel = sr.contiguous()
+        self.dr_face = t.randint(0, self.faces, (cells, 4), generator=g, device=dev, dtype=t.int64)
+        es = self.imposed_plus.element_size()
+        self.godunov_ptrs = (self.imposed_plus.data_ptr() + self.dr_face * (9 * ctx.ppad * es)).contiguous()
+        self.flux_solver_ptrs = (self.flux_solver.data_ptr() + self.dr_face * (81 * es)).contiguous()
+        self.dr_face_types = t.full((cells, 4), 3, dtype=t.uint8, device=dev)
+        # fault faces sorted by their (plus, minus) operator variants: uniform instruction stream per CTA
+        key = info[:, 0].to(t.int64) + 4 * (info[:, 1].to(t.int64) + 4 * info[:, 2].to(t.int64))
+        self.perm = t.argsort(key, stable=True).to(t.int32).contiguous()
+        pts, _ = gauss_legendre_points(ctx.order, TIMESTEP)
+        self.coeffs = np.stack([point_coeffs(ctx.order, tau) for tau in pts])
+
+    def der_array(self, cell_index):
+        stride = self.derivs.stride(0) * self.derivs.element_size()
+        self._keep = getattr(self, "_keep", [])
+        ptrs = (self.derivs.data_ptr() + cell_index * stride).contiguous()
+        self._keep.append(ptrs)
+        return api.pointer_table(ptrs)
+
+
+class DrProxyKernels(ProxyKernels):
+    """godunov_dr, neigh_dr, all_dr (src/Proxy/KernelHost.h:29-56)."""
+
+    def __init__(self, ctx, data, dr):
+        super().__init__(ctx, data)
+        self.dr = dr
+        self._plus = dr.der_array(dr.plus_cell)
+        self._minus = dr.der_array(dr.minus_cell)
+
+    def godunov_dr(self, stream=None):
+        r = self.dr
+        self.ctx.dr_interp(self._plus, self._minus, r.tinv_t, r.face_info, r.q_plus, r.q_minus, r.coeffs, r.faces,
+                           perm=r.perm, stream=stream)
+
+    def neigh_dr(self, stream=None):
+        r, d = self.dr, self.d
+        self.ctx.neigh_dr(api.strided(d.dofs), r.godunov_ptrs, r.flux_solver_ptrs, r.side_rel, r.dr_face_types,
+                          d.cells, stream=stream)
+
+    def all_dr(self, stream=None):
+        self.local(stream)
+        self.godunov_dr(stream)
+        self.neigh_dr(stream)
