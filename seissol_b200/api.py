@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libseissol_b200.so")
+# SSB_LIB selects a differently-configured build of the same library (A/B measurements, seissol_b200/build.py)
+LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(HERE, "lib", "libseissol_b200.so")
 
 SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",

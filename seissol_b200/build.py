@@ -28,7 +28,10 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=True, force=False, extra_flags=()):
+def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sources=None):
+    """variant: build a differently-configured library libseissol_b200_<variant>.so (development aid for
+    A/B measurements; selected at run time with the environment variable SSB_LIB).  Only the translation
+    units named in `variant_sources` are recompiled with `extra_flags`; the rest is linked from the main build."""
     sys.path.insert(0, os.path.join(HERE, "codegen"))
     import gen_ops  # noqa: E402
 
@@ -53,14 +56,25 @@ def build(verbose=True, force=False, extra_flags=()):
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     jobs = []
+    objdir = OBJDIR if variant is None else OBJDIR + "_" + variant
+    os.makedirs(objdir, exist_ok=True)
+    lib = LIB if variant is None else LIB.replace(".so", f"_{variant}.so")
+
+    def obj_of(src):
+        base = os.path.basename(src)
+        if variant is not None and (variant_sources is None or base in variant_sources):
+            return os.path.join(objdir, base[:-3] + ".o")
+        return os.path.join(OBJDIR, base[:-3] + ".o")
+
     for src in sources:
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        obj = obj_of(src)
         if force or _newer(obj, [src] + headers):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        cmd = ["nvcc", *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
+        flags = extra_flags if obj.startswith(objdir + os.sep) or variant is None else ()
+        cmd = ["nvcc", *NVCC_FLAGS, *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -71,15 +85,15 @@ def build(verbose=True, force=False, extra_flags=()):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
-    objs = [os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o") for s in sources]
-    if jobs or not os.path.exists(LIB):
-        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    objs = [obj_of(s) for s in sources]
+    if jobs or not os.path.exists(lib):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
-            print(f"[build] linked {LIB}", flush=True)
-    return LIB
+            print(f"[build] linked {lib}", flush=True)
+    return lib
 
 
 if __name__ == "__main__":

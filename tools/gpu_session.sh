@@ -1,0 +1,51 @@
+#!/bin/bash
+# One gpurun session: parity tests, micro-benchmarks, A/B kernel timings, bench.py, ncu captures.
+# usage: tools/gpu_session.sh <tag> [steps...]   (steps: test ubench qb qbdr bench ncu)
+tag=$1; shift
+steps=${@:-"test qb bench ncu"}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/env.txt 2>&1
+PK2=$PWD/seissol_b200/lib/libseissol_b200_pk2.so
+for s in $steps; do
+case $s in
+test)
+  timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "exit $?" >> $out/pytest.log ;;
+testpk2)
+  SSB_LIB=$PK2 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "6" > $out/pytest_pk2.log 2>&1; echo "exit $?" >> $out/pytest_pk2.log ;;
+ubench)
+  timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
+qb)
+  timeout 300 python tools/quick_bench.py > $out/qb.txt 2>&1
+  SSB_PERSISTENT=2 timeout 300 python tools/quick_bench.py > $out/qb_persist2.txt 2>&1
+  [ -f $PK2 ] && SSB_LIB=$PK2 timeout 300 python tools/quick_bench.py > $out/qb_pk2.txt 2>&1
+  [ -f $PK2 ] && SSB_PERSISTENT=1 SSB_LIB=$PK2 timeout 300 python tools/quick_bench.py > $out/qb_pk2_persist1.txt 2>&1
+  timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
+qbdr)
+  timeout 300 python tools/quick_bench_dr.py > $out/qbdr.txt 2>&1
+  timeout 300 python tools/quick_bench_dr.py --real 8 > $out/qbdr_f64.txt 2>&1 ;;
+bench)
+  timeout 900 python bench.py > $out/bench.json 2> $out/bench.err
+  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err ;;
+ncu)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu > $out/launches_bench.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 9 -c 3 -f -o $out/full \
+      python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_full.log 2>&1 ;;
+ncudr)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp|k_friction|k_neigh_dr' --launch-skip 5 -c 4 -f -o $out/full_dr \
+      python tools/quick_bench_dr.py --steps 1 > $out/ncu_full_dr.log 2>&1 ;;
+esac
+done
+# .ncu-rep files above 30 MB would push gpurun_out over its 64 MiB limit: keep the CSV pages instead
+for rep in $out/*.ncu-rep; do
+  [ -f "$rep" ] || continue
+  ncu -i $rep --page raw --csv > ${rep%.ncu-rep}_raw.csv 2>/dev/null
+  if [ $(stat -c %s $rep) -gt 30000000 ]; then
+    ncu -i $rep --page source --csv > ${rep%.ncu-rep}_source.csv 2>/dev/null
+    gzip -f ${rep%.ncu-rep}_source.csv
+    rm -f $rep
+  fi
+done
+ls -la $out
+for f in $out/*.log $out/*.txt $out/*.json $out/*.err; do echo "=== $f"; tail -c 1500 $f; done
