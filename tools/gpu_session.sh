@@ -25,7 +25,8 @@ qbdr)
   timeout 300 python tools/quick_bench_dr.py > $out/qbdr.txt 2>&1
   timeout 300 python tools/quick_bench_dr.py --real 8 > $out/qbdr_f64.txt 2>&1 ;;
 bench)
-  timeout 900 python bench.py > $out/bench.json 2> $out/bench.err
+  timeout 900 python bench.py > $out/bench.json 2> $out/bench.err ;;
+benchref)
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err ;;
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches.csv \
