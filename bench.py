@@ -3,10 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the proxy kernel over the whole synthetic element batch
-(`proxy <cells> <steps> all`, src/Proxy/Runner.cpp:93-111).  Workload at every N: BASELINE.json
-configs[1], elastic ORDER=6 single precision, 1M elements PER GPU (weak scaling; the proxy's
-fake topology has no cross-GPU faces, so ranks are independent replicas -- DESIGN.md §7).
+One "step" = one pass of the element update (`all` = ader + local + neigh) over the whole element batch.
+N = 1: BASELINE.json configs[1], the proxy (`proxy <cells> <steps> all`, src/Proxy/Runner.cpp:93-111), elastic
+ORDER=6 single precision, 1M synthetic elements with the proxy's random fake topology.
+N > 1: ONE cube mesh of ~1M tetrahedra PER GPU partitioned across the GPUs (BASELINE.json configs[4] at the
+per-GPU size of configs[1]; weak scaling): copy-layer buffers travel to the neighbouring rank's ghost layer over
+NCCL/NVLink while the interior elements are updated (seissol_b200/distributed.py).
+`--replicas` runs N independent proxy replicas instead.
 Prints ONE JSON line (rank 0).  Metric: element-updates/s (cells x steps / time), the
 reference's own proxy metric (src/Proxy/Runner.cpp:122-144), plus non-zero GFLOP/s.
 
@@ -310,6 +313,140 @@ def run_ours(args):
     return 0
 
 
+def run_partitioned(args):
+    """N > 1: ONE cube mesh partitioned across the GPUs (BASELINE.json configs[4] at a per-GPU size that matches
+    the single-GPU workload): slabs along x, copy/interior/ghost layers, halo exchange of the copy-layer buffers
+    over NCCL/NVLink overlapped with the interior element update (seissol_b200/distributed.py).  Weak scaling:
+    ~1M elements per GPU, global time stepping."""
+    import torch
+    import torch.distributed as dist
+    from seissol_b200 import api, proxy
+    from seissol_b200 import distributed as D
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=device)
+
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    ctx = api.Context(ORDER, args.real)
+    dtype = torch.float32 if args.real == 4 else torch.float64
+    # slab of nxl x ny x nz cubes (5 tetrahedra each) per GPU
+    ny, nz = 70, 72
+    nxl = max(2, int(round(args.cells / (5.0 * ny * nz))))
+    nxl += nxl % 2 if (nxl * world) % 2 else 0
+    nx = nxl * world
+    layout, data = D.build_partitioned(torch, dist, nx, ny, nz, rank, world, ctx.B, ctx.ld, dtype, device)
+    data.sort_by_face_relation()
+    coeffs = proxy.integrate_coeffs(ORDER, 0.0, proxy.TIMESTEP)
+    backend = D.CudaBackend(ctx, data, coeffs)
+    exchange = D.HaloExchange(torch, dist, layout, data.buffers)
+    solver = D.PartitionedSolver(torch, layout, data, backend, exchange, overlap=not args.no_overlap)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        solver.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    for _ in range(steps):
+        solver.step()
+    t_end.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    total_ms = t_begin.elapsed_time(t_end)
+    finite = bool(torch.isfinite(data.dofs).all())
+
+    # exchange alone (not overlapped), for the report
+    x0 = torch.cuda.Event(enable_timing=True)
+    x1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    x0.record(stream)
+    for _ in range(5):
+        exchange.exchange()
+    x1.record(stream)
+    barrier()
+    exch_ms = x0.elapsed_time(x1) / 5
+
+    # ---- end to end: DOFs of the own cells host -> device, one step, device -> host, every step
+    e2e_steps = max(1, min(steps, 5))
+    h_in = torch.empty(data.dofs.shape, dtype=data.dofs.dtype, pin_memory=True)
+    h_in.copy_(data.dofs)
+    h_out = torch.empty_like(h_in, pin_memory=True)
+    for _ in range(2):
+        data.dofs.copy_(h_in, non_blocking=True)
+        solver.step()
+        h_out.copy_(data.dofs, non_blocking=True)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        data.dofs.copy_(h_in, non_blocking=True)
+        solver.step()
+        h_out.copy_(data.dofs, non_blocking=True)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    red = torch.tensor([total_ms, e2e_ms, exch_ms], device=device, dtype=torch.float64)
+    dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, exch_ms = (float(v) for v in red.tolist())
+    cnt = torch.tensor([layout.n_own, layout.n_copy, layout.n_ghost], device=device, dtype=torch.int64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    cells_total, copy_total, ghost_total = (int(v) for v in cnt.tolist())
+    io_bytes = data.dofs.numel() * data.dofs.element_size()
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        ms_per_step = total_ms / steps
+        value = cells_total / (ms_per_step * 1e-3)
+        nz = proxy.nz_flops_per_element(ORDER, KERNEL)
+        all_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, KERNEL)
+        achieved = all_bytes * cells_total / world / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "element-updates/s", "value": value, "unit": "element-updates/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.real == 4 else "f64", "data": "synthetic",
+            "gflops_nz": value * nz * 1e-9,
+            "config": {"workload": f"cube mesh {nx}x{ny}x{nz} cubes x 5 tetrahedra = {cells_total} elements, elastic ORDER={ORDER} "
+                                   f"{'single' if args.real == 4 else 'double'}, element update `all` (ader+local+neigh), "
+                                   f"global time stepping, x-slab partition over {world} GPUs with NVLink halo exchange "
+                                   "(BASELINE.json configs[4] at the per-GPU size of configs[1])",
+                       "cells_per_gpu": cells_total // world, "copy_cells": copy_total, "ghost_cells": ghost_total,
+                       "halo_bytes_per_step_per_gpu": exchange.bytes_per_exchange,
+                       "halo_exchange_ms_alone": exch_ms, "overlap": solver.overlap,
+                       "l2": "inputs exceed L2 (%.1f GiB resident per GPU)" % (
+                           sum(x.numel() * x.element_size() for x in (data.dofs, data.buffers, data.local_int, data.neigh_int)) / 2 ** 30),
+                       "parallelism": f"mesh partition x{world}, NCCL send/recv of copy-layer buffers", "finite": finite},
+            "roofline": {"bound": "hbm", "kernel": "step (k_local<ader> + k_local<localwoader> + k_neigh per layer)",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_kind": peak_kind, "per": "GPU"},
+            "e2e": {"value": cells_total * e2e_steps / (e2e_ms * 1e-3), "unit": "element-updates/s",
+                    "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world, "steps": e2e_steps,
+                    "what": "per step and GPU: DOFs pinned host -> device, partitioned element update through the C ABI "
+                            "(incl. halo exchange), DOFs device -> pinned host"},
+            "gpu_launches": backend.launches_per_step * steps,
+            "clocks": sampler.result(),
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,9 +456,13 @@ def main():
     ap.add_argument("--cells", type=int, default=CELLS)
     ap.add_argument("--real", type=int, default=REAL, choices=[4, 8])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent proxy replicas instead of the partitioned mesh")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.replicas:
+        return run_partitioned(args)
     return run_ours(args)
 
 

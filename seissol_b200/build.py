@@ -55,6 +55,12 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
         glob.glob(os.path.join(CSRC, "gen", "*.cuh")) + \
         glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    # generation-4 kernels are the product path in double precision only; the single-precision instantiations
+    # (slower than generation 3) are built on request for A/B measurements
+    v4_f32 = os.environ.get("SSB_BUILD_V4_F32") == "1"
+    if not v4_f32:
+        sources = [s for s in sources if not (os.path.basename(s).startswith("inst4_") and s.endswith("_f32.cu"))]
+    extra_flags = tuple(extra_flags) + (("-DSSB_HAVE_V4_F32",) if v4_f32 else ())
     jobs = []
     objdir = OBJDIR if variant is None else OBJDIR + "_" + variant
     os.makedirs(objdir, exist_ok=True)
@@ -74,6 +80,8 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
     def compile_one(job):
         src, obj = job
         flags = extra_flags if obj.startswith(objdir + os.sep) or variant is None else ()
+        if v4_f32 and "-DSSB_HAVE_V4_F32" not in flags:
+            flags = tuple(flags) + ("-DSSB_HAVE_V4_F32",)
         cmd = ["nvcc", *NVCC_FLAGS, *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

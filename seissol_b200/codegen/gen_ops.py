@@ -149,8 +149,30 @@ def gen_spmv_reg(em, fname, m, in_pad, out_pad, accumulate):
     return nfma
 
 
+def gen_spmv_chunks(em, fname, m, in_pad, out_pad):
+    """out += M . x where x arrives in chunks of 4 entries from a kernel-supplied source
+    (js.template chunk<c>(x4) yields x[4c .. 4c+3]): the full x column never sits in registers."""
+    em.w("template <typename R, typename JS>")
+    em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const JS& js) {{")
+    nfma = 0
+    rows, cols = m.shape
+    for c in range(in_pad // 4):
+        ls = [l for l in range(4 * c, min(4 * c + 4, cols)) if np.any(m[:, l] != 0)]
+        if not ls:
+            continue
+        em.w(f"  {{ typename Pk<R>::T x[4]; js.template chunk<{c}>(x);")
+        for l in ls:
+            for k in np.nonzero(m[:, l])[0]:
+                emit_acc(em, None, "out", int(k), m[k, l], f"x[{l - 4 * c}]")
+                nfma += 1
+        em.w("  }")
+    em.w("}")
+    em.w()
+    return nfma
+
+
 def gen_dispatch(em, base, count, sig_decl, sig_call, src=False):
-    em.w("template <typename R, typename Src>" if src else "template <typename R>")
+    em.w(f"template <typename R, typename {src}>" if src else "template <typename R>")
     em.w(f"__device__ __forceinline__ void {base}(int i, {sig_decl}) {{")
     em.w("  switch (i) {")
     for i in range(count):
@@ -191,13 +213,13 @@ def generate(order):
     for f in range(4):
         stats[f"fMrT_{f}"] = gen_spmv_smem(em, f"fMrT_{f}", z["fMrT"][f], pad4(B2), False)
         stats[f"rT_{f}"] = gen_spmv_smem(em, f"rT_{f}", z["rT"][f], pad4(B2), False)
-        stats[f"rDivM_{f}"] = gen_spmv_reg(em, f"rDivM_{f}", z["rDivM"][f], pad4(B2), pad4(B), True)
+        stats[f"rDivM_{f}"] = gen_spmv_chunks(em, f"rDivM_{f}", z["rDivM"][f], pad4(B2), pad4(B))
     for h in range(3):
         stats[f"fP_{h}"] = gen_spmv_reg(em, f"fP_{h}", z["fP"][h], pad4(B2), pad4(B2), False)
     PT = "typename Pk<R>::T"
-    gen_dispatch(em, "fMrT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src=True)
-    gen_dispatch(em, "rT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src=True)
-    gen_dispatch(em, "rDivM", 4, f"{PT} (&out)[{pad4(B)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
+    gen_dispatch(em, "fMrT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src="Src")
+    gen_dispatch(em, "rT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src="Src")
+    gen_dispatch(em, "rDivM", 4, f"{PT} (&out)[{pad4(B)}], const JS& js", "out, js", src="JS")
     gen_dispatch(em, "fP", 3, f"{PT} (&out)[{pad4(B2)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
     # --- ADER driver: the kernel supplies a context with src()/finish() (hand-written)
     em.w("template <typename R, typename Ctx>")

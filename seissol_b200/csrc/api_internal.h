@@ -44,5 +44,12 @@ const KernelSet* kernelset_o6_f32();
 const KernelSet* kernelset_o4_f64();
 const KernelSet* kernelset_o5_f64();
 const KernelSet* kernelset_o6_f64();
+// kernel generation 4: half-column threads (kernels_elastic4.cuh)
+const KernelSet* kernelset4_o4_f32();
+const KernelSet* kernelset4_o5_f32();
+const KernelSet* kernelset4_o6_f32();
+const KernelSet* kernelset4_o4_f64();
+const KernelSet* kernelset4_o5_f64();
+const KernelSet* kernelset4_o6_f64();
 
 }  // namespace ssb

@@ -1,6 +1,7 @@
 // C ABI of libseissol_b200.so (declared in include/seissol_b200.h).  Thin argument
 // validation + dispatch onto the per-(order, real) kernel instantiations.  No CPU path.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -9,8 +10,12 @@
 
 using namespace ssb;
 
+
 struct ssb_ctx {
-  const KernelSet* ks;
+  const KernelSet* ks;       // query + taylor + default
+  const KernelSet* ksAder;   // predictor alone
+  const KernelSet* ksLocal;  // volume + local flux (with or without the predictor)
+  const KernelSet* ksNeigh;
   const DrKernelSet* dr;
   int ppad;
   int order;
@@ -74,6 +79,41 @@ const DrKernelSet* lookupDr(int order, int realSize) {
       case 4: return drkernelset_o4_f64();
       case 5: return drkernelset_o5_f64();
       case 6: return drkernelset_o6_f64();
+      default: return nullptr;
+    }
+  }
+  return nullptr;
+}
+
+// Kernel generation per entry point: 3 = full-column threads (kernels_elastic.cuh), 4 = half-column threads
+// (kernels_elastic4.cuh).  Defaults from the measurements in DESIGN.md §5: single precision runs generation 3
+// everywhere; double precision runs the predictor on generation 3 (255 registers, no spills) and
+// volume/local flux/neighbor flux on generation 4 (generation 3 needs > 255 registers there).  The environment
+// variable SSB_KGEN = 3 | 4 forces one generation for everything (A/B measurements only).
+int forcedGeneration() {
+  const char* e = std::getenv("SSB_KGEN");
+  if (e != nullptr && (e[0] == '3' || e[0] == '4')) {
+    return e[0] - '0';
+  }
+  return 0;
+}
+
+const KernelSet* lookup4(int order, int realSize) {
+#ifdef SSB_HAVE_V4_F32
+  if (realSize == 4) {
+    switch (order) {
+      case 4: return kernelset4_o4_f32();
+      case 5: return kernelset4_o5_f32();
+      case 6: return kernelset4_o6_f32();
+      default: return nullptr;
+    }
+  }
+#endif
+  if (realSize == 8) {
+    switch (order) {
+      case 4: return kernelset4_o4_f64();
+      case 5: return kernelset4_o5_f64();
+      case 6: return kernelset4_o6_f64();
       default: return nullptr;
     }
   }
@@ -154,7 +194,15 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
   if (c == nullptr) {
     return SSB_EINVAL;
   }
+  const KernelSet* ks4 = lookup4(order, real_size);
+  const int forced = forcedGeneration();
   c->ks = ks;
+  c->ksAder = ks;
+  c->ksLocal = (real_size == 8 && ks4 != nullptr) ? ks4 : ks;
+  c->ksNeigh = c->ksLocal;
+  if (forced == 3 || (forced == 4 && ks4 != nullptr)) {
+    c->ks = c->ksAder = c->ksLocal = c->ksNeigh = forced == 4 ? ks4 : ks;
+  }
   c->dr = lookupDr(order, real_size);
   c->ppad = c->dr != nullptr ? c->dr->PP : 0;
   c->order = order;
@@ -212,8 +260,8 @@ int ssb_query(const ssb_ctx* c, int* out) {
     out[4 + d] = c->derOffset[d];
     out[12 + d] = c->derLd[d];
   }
-  out[20] = c->ks->eLocal;
-  out[21] = c->ks->eNeigh;
+  out[20] = c->ksLocal->eLocal;
+  out[21] = c->ksNeigh->eNeigh;
   out[22] = c->dr != nullptr ? c->dr->P : 0;
   out[23] = c->ppad;
   return 0;
@@ -229,7 +277,7 @@ int ssb_ader(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs
   if (rc != 0) {
     return rc;
   }
-  return c->ks->local(p, true, false, static_cast<cudaStream_t>(stream));
+  return c->ksAder->local(p, true, false, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t local_int,
@@ -240,7 +288,7 @@ int ssb_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t local
   if (rc != 0) {
     return rc;
   }
-  return c->ks->local(p, false, true, static_cast<cudaStream_t>(stream));
+  return c->ksLocal->local(p, false, true, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_ader_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs,
@@ -254,7 +302,7 @@ int ssb_ader_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t 
   if (rc != 0) {
     return rc;
   }
-  return c->ks->local(p, true, true, static_cast<cudaStream_t>(stream));
+  return c->ksLocal->local(p, true, true, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* coeffs, long long n,
@@ -309,7 +357,7 @@ int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const lo
   p.perm = perm;
   p.n = n;
   p.ldg = c->ldq;
-  return c->ks->neigh(p, static_cast<cudaStream_t>(stream));
+  return c->ksNeigh->neigh(p, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_set_dr_layout(ssb_ctx* c, int ppad) {

@@ -175,11 +175,39 @@ __device__ __forceinline__ void stv4(float* p, float2 a, float2 b, float2 c, flo
 }
 __device__ __forceinline__ void stv4(double* p, double a, double b, double c, double d) { st4(p, a, b, c, d); }
 
+// 2 consecutive packed entries (one 128-bit access for float2 / double, 64-bit for scalar float)
+__device__ __forceinline__ void ldv2(float2 (&v)[2], const float* p) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+}
+__device__ __forceinline__ void ldv2(float (&v)[2], const float* p) {
+  const float2 a = *reinterpret_cast<const float2*>(p);
+  v[0] = a.x; v[1] = a.y;
+}
+__device__ __forceinline__ void ldv2(double (&v)[2], const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  v[0] = a.x; v[1] = a.y;
+}
+__device__ __forceinline__ void stv2(float* p, float2 a, float2 b) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void stv2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void stv2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+// lane v of 2 packed values -> 2 consecutive reals
+__device__ __forceinline__ void st2lane(float* p, int v, float2 a, float2 b) {
+  *reinterpret_cast<float2*>(p) = v == 0 ? make_float2(a.x, b.x) : make_float2(a.y, b.y);
+}
+__device__ __forceinline__ void st2lane(float* p, int, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2lane(double* p, int, double a, double b) {
+  *reinterpret_cast<double2*>(p) = make_double2(a, b);
+}
+
 // Operand sources of the generated sparse mat-vec code: a lane-interleaved column, or V
 // separate per-element columns (TMA landing zones) packed on the fly.
 template <typename R> struct SrcPk {
   const R* p;
   __device__ __forceinline__ void load4(typename Pk<R>::T (&v)[4], int k0) const { ldv4(v, p + k0 * Pk<R>::V); }
+  __device__ __forceinline__ void load2(typename Pk<R>::T (&v)[2], int k0) const { ldv2(v, p + k0 * Pk<R>::V); }
 };
 template <typename R> struct SrcSplit;
 template <> struct SrcSplit<float> {
@@ -191,10 +219,17 @@ template <> struct SrcSplit<float> {
     v[2] = make_float2(a.z, b.z); v[3] = make_float2(a.w, b.w);
   }
   __device__ __forceinline__ void load4(float (&v)[4], int k0) const { ld4(v, p0 + k0); }
+  __device__ __forceinline__ void load2(float2 (&v)[2], int k0) const {
+    const float2 a = *reinterpret_cast<const float2*>(p0 + k0);
+    const float2 b = *reinterpret_cast<const float2*>(p1 + k0);
+    v[0] = make_float2(a.x, b.x); v[1] = make_float2(a.y, b.y);
+  }
+  __device__ __forceinline__ void load2(float (&v)[2], int k0) const { ldv2(v, p0 + k0); }
 };
 template <> struct SrcSplit<double> {
   const double* p0; const double* p1;
   __device__ __forceinline__ void load4(double (&v)[4], int k0) const { ld4(v, p0 + k0); }
+  __device__ __forceinline__ void load2(double (&v)[2], int k0) const { ldv2(v, p0 + k0); }
 };
 // lane v of 4 packed values -> one 128-bit (float) / 256-bit (double) store
 __device__ __forceinline__ void st4lane(float* p, int v, float2 a, float2 b, float2 c, float2 d) {

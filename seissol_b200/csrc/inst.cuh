@@ -54,9 +54,9 @@ struct Gen {
   __device__ __forceinline__ static void rT(int f, typename Pk<R>::T (&out)[kB2P], const Src& x) {
     SSB_GEN::rT<R>(f, out, x);
   }
-  template <typename R>
-  __device__ __forceinline__ static void rDivM(int f, typename Pk<R>::T (&out)[kBP], const typename Pk<R>::T (&x)[kB2P]) {
-    SSB_GEN::rDivM<R>(f, out, x);
+  template <typename R, typename JS>
+  __device__ __forceinline__ static void rDivM(int f, typename Pk<R>::T (&out)[kBP], const JS& js) {
+    SSB_GEN::rDivM<R>(f, out, js);
   }
   template <typename R>
   __device__ __forceinline__ static void fP(int h, typename Pk<R>::T (&out)[kB2P], const typename Pk<R>::T (&x)[kB2P]) {

@@ -25,15 +25,13 @@ struct GenDr {
   __device__ __forceinline__ static void V3mTo2n(int i, PT (&out)[kPP], const Src& x) {
     SSB_GEN_DR::V3mTo2n<PT>(i, out, x);
   }
-  template <typename PT>
-  __device__ __forceinline__ static void V3mTo2nTWDivM(int i, PT (&out)[GenO::kBP], const PT (&x)[kPP]) {
-    SSB_GEN_DR::V3mTo2nTWDivM<PT>(i, out, x);
-  }
+  template <typename R>
+  __device__ __forceinline__ static const R* nodalFluxTable() { return SSB_GEN_DR::nodalFluxTable<R>(); }
 };
 
 using Real = SSB_REAL;
 constexpr int NF = sizeof(SSB_REAL) == 8 ? 4 : 8;  // faces per CTA (k_dr_interp): <= 256 threads, 255 registers
-constexpr int END = 14;  // elements per CTA (k_neigh_dr)
+constexpr int NDW = sizeof(SSB_REAL) == 8 ? 4 : 8;  // warps = elements per CTA (k_neigh_dr); static shared memory <= 48 KB
 
 template <typename K>
 int setSmem(K kern, size_t bytes, size_t& configured) {
@@ -81,15 +79,8 @@ int neighDrEntry(const NeighDrParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
-  auto kern = k_neigh_dr<Real, GenO, GenDr, END>;
-  const int tileStride = padOdd16(9 * (p.ppad > GenO::kBP ? p.ppad : GenO::kBP), sizeof(Real));
-  const size_t bytes = ((size_t(END) * tileStride * sizeof(Real) + 15) / 16) * 16 + 16;
-  static size_t configured = 0;
-  if (int rc = setSmem(kern, bytes, configured)) {
-    return rc;
-  }
-  const unsigned grid = unsigned((p.n + END - 1) / END);
-  kern<<<grid, (9 * END + 31) / 32 * 32, bytes, stream>>>(p);
+  const unsigned grid = unsigned((p.n + NDW - 1) / NDW);
+  k_neigh_dr<Real, GenO, GenDr, NDW><<<grid, 32 * NDW, 0, stream>>>(p);
   return int(cudaGetLastError());
 }
 

@@ -559,124 +559,111 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
 
 // ---------------------------------------------------------------------------------------
 // Nodal flux of dynamic-rupture faces: Q += V3mTo2nTWDivM(side, rel) . (godunov . fluxSolver).
-// A CTA owns E elements, thread (e, q) owns column q; the imposed state of the current face is staged in shared
-// memory by a bulk copy, Q is read-modified-written through the same tile at the end.
-template <typename R, typename G, typename GD, int E>
-__global__ void __launch_bounds__((9 * E + 31) / 32 * 32) k_neigh_dr(const NeighDrParams p) {
-  constexpr int BP = G::kBP, PP = GD::kPP;
-  extern __shared__ __align__(128) unsigned char smemRaw[];
-  R* const smem = reinterpret_cast<R*>(smemRaw);
-  const int tileStride = padOdd16(9 * (p.ppad > BP ? p.ppad : BP), sizeof(R));
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + ((size_t(E) * tileStride * sizeof(R) + 15) / 16) * 16);
-  const int tid = threadIdx.x;
-  const bool active = tid < 9 * E;
-  const int e = active ? tid % E : 0;
-  const int q = active ? tid / E : 0;
-  const long long sl = static_cast<long long>(blockIdx.x) * E + e;
-  const long long el = sl < p.n ? sl : -1;
-  if (tid == 0) {
-    mbar_init(bar, E);
-    mbar_fence_init();
+//
+// V3mTo2nTWDivM is the one DENSE operator of the path (B x P, 56 x 49 at order 6, 16 (side, relation) variants),
+// and the variant differs from element to element, so immediate-operand code would diverge 16-fold inside a
+// warp.  Instead: ONE WARP PER ELEMENT, the operator read from a dense table in global memory
+// ([variant][point][64], basis index fastest: coalesced, L1/L2 resident, 200 KB in single precision), lane l
+// owns the rows l and l + 32 of all nine quantity columns (18 accumulators).  Per DR face:
+//   1. T[p][q] = sum_c godunov[c][p] fluxSolver[c][q]   (lane = point, coalesced reads of the imposed state)
+//   2. acc[k][q] += sum_p W[p][k] T[p][q]                (T broadcast from shared memory, W coalesced)
+// and finally Q[k][q] += acc[k][q] with coalesced read-modify-writes.
+template <typename R, typename G, typename GD, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_neigh_dr(const NeighDrParams p) {
+  constexpr int B = G::kB, P = GD::kP;
+  constexpr int TS = 12;  // reals per point of T in shared memory (9 padded to 12: three 128-bit words)
+  __shared__ __align__(16) R sT[WARPS][2 * 32 * TS];
+  __shared__ __align__(16) R sFs[WARPS][84];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long el = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  if (el >= p.n) {
+    return;
   }
-  __syncthreads();
-  R* const tile = smem + e * tileStride;
-  uint8_t ft[4] = {0, 0, 0, 0};
-  if (el >= 0 && p.faceTypes != nullptr) {
-    const uchar4 t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
-    ft[0] = t.x; ft[1] = t.y; ft[2] = t.z; ft[3] = t.w;
-  }
-  R acc[BP];
+  const R* const table = GD::template nodalFluxTable<R>();
+  const uchar4 ft = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
+  R acc[2][9];
 #pragma unroll
-  for (int k = 0; k < BP; ++k) {
-    acc[k] = R(0);
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      acc[r][q] = R(0);
+    }
   }
-  uint32_t phase = 0;
+  bool any = false;
 #pragma unroll 1
   for (int f = 0; f < 4; ++f) {
-    const bool dr = el >= 0 && ft[f] == 3 && p.godunov[4 * el + f] != nullptr;
-    if (tid < E) {  // e == tid
-      if (dr) {
-        mbar_arrive_expect_tx(bar, 9 * p.ppad * sizeof(R));
-        tma_load(tile, p.godunov[4 * el + f], 9 * p.ppad * sizeof(R), bar);
-      } else {
-        mbar_arrive_expect_tx(bar, 0);
-      }
+    const uint8_t ty = f == 0 ? ft.x : (f == 1 ? ft.y : (f == 2 ? ft.z : ft.w));
+    const R* god = static_cast<const R*>(p.godunov[4 * el + f]);
+    if (ty != 3 || god == nullptr) {
+      continue;  // warp-uniform
     }
-    R fs[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      fs[c] = dr ? static_cast<const R*>(p.fluxSolver[4 * el + f])[c + 9 * q] : R(0);
+    any = true;
+    const R* fs = static_cast<const R*>(p.fluxSolver[4 * el + f]);
+    const int variant = p.sideRel[8 * el + 2 * f] + 4 * p.sideRel[8 * el + 2 * f + 1];
+    __syncwarp();
+    for (int i = lane; i < 81; i += 32) {
+      sFs[warp][i] = fs[i];
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    if (__syncthreads_or(dr)) {
-      R tmp[PP];
+    __syncwarp();
+    // ---- step 1: T = godunov . fluxSolver for the points lane, lane + 32
 #pragma unroll
-      for (int pp = 0; pp < PP; ++pp) {
-        tmp[pp] = R(0);
+    for (int half = 0; half < 2; ++half) {
+      const int pt = lane + 32 * half;
+      R t[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        t[q] = R(0);
       }
-      if (dr) {
+      if (pt < P) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
+          const R gv = god[c * p.ppad + pt];
 #pragma unroll
-          for (int p4 = 0; p4 < PP / 4; ++p4) {
-            R t[4];
-            ld4(t, tile + c * p.ppad + 4 * p4);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              tmp[4 * p4 + i] = fma(fs[c], t[i], tmp[4 * p4 + i]);
-            }
+          for (int q = 0; q < 9; ++q) {
+            t[q] = fma(gv, sFs[warp][c + 9 * q], t[q]);
           }
         }
+      }
+      R* dst = &sT[warp][pt * TS];
+      st4(dst, t[0], t[1], t[2], t[3]);
+      st4(dst + 4, t[4], t[5], t[6], t[7]);
+      st4(dst + 8, t[8], R(0), R(0), R(0));
+    }
+    __syncwarp();
+    // ---- step 2: acc += W(variant) . T
+    const R* w = table + static_cast<size_t>(variant) * P * 64 + lane;
+#pragma unroll 7
+    for (int pt = 0; pt < P; ++pt) {
+      const R w0 = w[pt * 64];
+      const R w1 = w[pt * 64 + 32];
+      R t[12];
+      {
+        R u[4];
+        ld4(u, &sT[warp][pt * TS]);     t[0] = u[0]; t[1] = u[1]; t[2] = u[2]; t[3] = u[3];
+        ld4(u, &sT[warp][pt * TS + 4]); t[4] = u[0]; t[5] = u[1]; t[6] = u[2]; t[7] = u[3];
+        ld4(u, &sT[warp][pt * TS + 8]); t[8] = u[0];
+      }
 #pragma unroll
-        for (int pp = GD::kP; pp < PP; ++pp) {
-          tmp[pp] = R(0);  // padding points carry no flux
-        }
-        const int variant = p.sideRel[8 * el + 2 * f] + 4 * p.sideRel[8 * el + 2 * f + 1];
-        GD::template V3mTo2nTWDivM<R>(variant, acc, tmp);
+      for (int q = 0; q < 9; ++q) {
+        acc[0][q] = fma(w0, t[q], acc[0][q]);
+        acc[1][q] = fma(w1, t[q], acc[1][q]);
       }
     }
-    __syncthreads();  // the tile is re-used by the next face
   }
-  // Q += acc through the tile
-  if (tid < E) {
-    if (el >= 0) {
-      mbar_arrive_expect_tx(bar, 9 * BP * sizeof(R));
-      const R* src = static_cast<const R*>(p.dofs.at(el));
-      if (p.ldg == BP) {
-        tma_load(tile, src, 9 * BP * sizeof(R), bar);
-      } else {
-        for (int c = 0; c < 9; ++c) {
-          tma_load(tile + c * BP, src + c * p.ldg, BP * sizeof(R), bar);
-        }
-      }
-    } else {
-      mbar_arrive_expect_tx(bar, 0);
-    }
+  if (!any) {
+    return;
   }
-  mbar_wait(bar, phase);
-  if (active && el >= 0) {
+  R* const dofs = static_cast<R*>(const_cast<void*>(p.dofs.at(el)));
 #pragma unroll
-    for (int k4 = 0; k4 < BP / 4; ++k4) {
-      R t[4];
-      ld4(t, tile + q * BP + 4 * k4);
-      st4(tile + q * BP + 4 * k4, t[0] + acc[4 * k4], t[1] + acc[4 * k4 + 1], t[2] + acc[4 * k4 + 2],
-          t[3] + acc[4 * k4 + 3]);
-    }
-  }
-  fence_async_smem();
-  __syncthreads();
-  if (tid < E && el >= 0) {
-    R* dst = static_cast<R*>(const_cast<void*>(p.dofs.at(el)));
-    if (p.ldg == BP) {
-      tma_store(dst, tile, 9 * BP * sizeof(R));
-    } else {
-      for (int c = 0; c < 9; ++c) {
-        tma_store(dst + c * p.ldg, tile + c * BP, BP * sizeof(R));
+  for (int r = 0; r < 2; ++r) {
+    const int k = lane + 32 * r;
+    if (k < B) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        dofs[q * p.ldg + k] += acc[r][q];
       }
     }
-    tma_store_commit();
-    tma_store_wait_read();
   }
 }
 

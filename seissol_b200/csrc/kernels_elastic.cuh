@@ -148,6 +148,28 @@ struct AderCtx {
   }
 };
 
+// J = F . A in chunks of 4 rows for the generated rDivM code: chunk c = rows 4c..4c+3 of column q of
+// (F . AplusT/AminusT), F interleaved in shared memory ([c][k][V]), a = column q of the 9x9 flux matrix.
+template <typename R, int B2P>
+struct JChunks {
+  using PT = typename Pk<R>::T;
+  static constexpr int V = Pk<R>::V;
+  const R* Fe;
+  const PT (&a)[kNQ];
+  template <int C>
+  __device__ __forceinline__ void chunk(PT (&x)[4]) const {
+#pragma unroll
+    for (int c = 0; c < kNQ; ++c) {
+      PT t[4];
+      ldv4(t, Fe + (c * B2P + 4 * C) * V);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[i] = c == 0 ? pk_mul(a[c], t[i]) : pk_fma(a[c], t[i], x[i]);
+      }
+    }
+  }
+};
+
 // own column q of the V staged element tensors of a group -> packed registers
 template <typename R, int BP, int TEN>
 __device__ __forceinline__ void loadStagedColumn(typename Pk<R>::T (&col)[BP], const R* staged, int q) {
@@ -392,41 +414,39 @@ __global__ void __launch_bounds__(blockThreads(NP), 2) k_local(const LocalParams
     // ---- local flux: Q += rDivM_f . ((fMrT_f . I) . AplusT_f), skipped on DR faces
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      // column q of AplusT_f straight from global memory; latency hidden by fMrT
+      // column q of AplusT_f straight from global memory; latency hidden by fMrT (single precision) --
+      // in double precision the registers are needed for the accumulators, so it is loaded after fMrT
       PT a[kNQ];
+      auto loadA = [&]() {
 #pragma unroll
-      for (int c = 0; c < kNQ; ++c) {
-        R t[V];
+        for (int c = 0; c < kNQ; ++c) {
+          R t[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          t[v] = skipFace[f][v] ? R(0) : LIg[v][72 + 81 * f + 9 * q + c];
+          for (int v = 0; v < V; ++v) {
+            t[v] = skipFace[f][v] ? R(0) : LIg[v][72 + 81 * f + 9 * q + c];
+          }
+          a[c] = pk_make(t);
         }
-        a[c] = pk_make(t);
+      };
+      if constexpr (sizeof(R) == 4) {
+        loadA();
       }
-      PT F[B2P];
-      G::template fMrT<R>(f, F, SrcPk<R>{Ie + q * BP * V});
       R* const Fe = RQ + (f & 1) * kNQ * B2P * V;
-      if (active) {
+      {
+        PT F[B2P];
+        G::template fMrT<R>(f, F, SrcPk<R>{Ie + q * BP * V});
+        if (active) {
 #pragma unroll
-        for (int k4 = 0; k4 < B2P / 4; ++k4) {
-          stv4(Fe + (q * B2P + 4 * k4) * V, F[4 * k4], F[4 * k4 + 1], F[4 * k4 + 2], F[4 * k4 + 3]);
-        }
-      }
-      __syncthreads();
-      PT J[B2P];
-#pragma unroll
-      for (int c = 0; c < kNQ; ++c) {
-#pragma unroll
-        for (int k4 = 0; k4 < B2P / 4; ++k4) {
-          PT t[4];
-          ldv4(t, Fe + (c * B2P + 4 * k4) * V);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            J[4 * k4 + i] = c == 0 ? pk_mul(a[c], t[i]) : pk_fma(a[c], t[i], J[4 * k4 + i]);
+          for (int k4 = 0; k4 < B2P / 4; ++k4) {
+            stv4(Fe + (q * B2P + 4 * k4) * V, F[4 * k4], F[4 * k4 + 1], F[4 * k4 + 2], F[4 * k4 + 3]);
           }
         }
       }
-      G::template rDivM<R>(f, acc, J);
+      if constexpr (sizeof(R) == 8) {
+        loadA();
+      }
+      __syncthreads();
+      G::template rDivM<R>(f, acc, JChunks<R, B2P>{Fe, a});
     }
 
     // ---- Q_new staged per element in RD (the last reader of I passed the barrier of face 3)
@@ -635,20 +655,7 @@ __global__ void __launch_bounds__(blockThreads(NP), 2) k_neigh(const NeighParams
       // next neighbor, or finally the element's own Q
       loadTile(f < 3 ? neighborOf(f + 1) : (myElem >= 0 ? static_cast<const R*>(p.dofs.at(myElem)) : nullptr));
     }
-    PT J[B2P];
-#pragma unroll
-    for (int c = 0; c < kNQ; ++c) {
-#pragma unroll
-      for (int k4 = 0; k4 < B2P / 4; ++k4) {
-        PT t[4];
-        ldv4(t, Fe + (c * B2P + 4 * k4) * V);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          J[4 * k4 + i] = c == 0 ? pk_mul(a[c], t[i]) : pk_fma(a[c], t[i], J[4 * k4 + i]);
-        }
-      }
-    }
-    G::template rDivM<R>(f, acc, J);
+    G::template rDivM<R>(f, acc, JChunks<R, B2P>{Fe, a});
   }
 
   // Q += acc: the own Q tensors arrived in the tiles

@@ -13,6 +13,20 @@ test)
   timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "exit $?" >> $out/pytest.log ;;
 testpk2)
   SSB_LIB=$PK2 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "6" > $out/pytest_pk2.log 2>&1; echo "exit $?" >> $out/pytest_pk2.log ;;
+v4)
+  NP7=$PWD/seissol_b200/lib/libseissol_b200_np7.so
+  SSB_KGEN=4 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_v4.log 2>&1; echo "exit $?" >> $out/pytest_v4.log
+  timeout 300 python tools/quick_bench.py > $out/qb_f32_v3.txt 2>&1
+  SSB_KGEN=4 timeout 300 python tools/quick_bench.py > $out/qb_f32_v4.txt 2>&1
+  [ -f $NP7 ] && SSB_LIB=$NP7 SSB_KGEN=4 timeout 300 python tools/quick_bench.py > $out/qb_f32_v4_np7.txt 2>&1
+  timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v4.txt 2>&1
+  [ -f $NP7 ] && SSB_LIB=$NP7 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v4_np7.txt 2>&1
+  SSB_KGEN=3 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v3.txt 2>&1 ;;
+qbf64)
+  timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
+part)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $out/bench_part2.json 2> $out/bench_part2.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-overlap > $out/bench_part2_noov.json 2> $out/bench_part2_noov.err ;;
 ubench)
   timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
 qb)
@@ -33,6 +47,11 @@ ncu)
       python bench.py --steps 2 --warmup 3 --no-cpu > $out/launches_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 9 -c 3 -f -o $out/full \
       python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_full.log 2>&1 ;;
+ncu2)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 6 -c 3 -f -o $out/full_f32 \
+      python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_full_f32.log 2>&1
+  SSB_KGEN=3 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 6 -c 3 -f -o $out/full_f64v3 \
+      python tools/quick_bench.py --real 8 --cells 148000 --steps 1 --kernels all > $out/ncu_full_f64v3.log 2>&1 ;;
 ncudr)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp|k_friction|k_neigh_dr' --launch-skip 5 -c 4 -f -o $out/full_dr \
       python tools/quick_bench_dr.py --steps 1 > $out/ncu_full_dr.log 2>&1 ;;
