@@ -160,6 +160,27 @@ int ssb_friction_rsfvw(ssb_ctx* ctx, const ssb_friction_data_t* data, const ssb_
 int ssb_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, const void* const* godunov, const void* const* flux_solver,
                  const uint8_t* side_rel, const uint8_t* face_types, long long n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * viscoelastic2 (anelastic attenuation; context created with equation = 1, mechanisms = 3, order 5).
+ * Additional per-element arrays: dofs_ane = Qane [M][6][ld] (LTS::DofsAne), idofs_ane = time-integrated memory
+ * variables Iane (LocalTmp::timeIntegratedAne of the reference, here a caller-provided array because ader and
+ * local are separate launches); local_int = LocalIntegrationData of the viscoelastic2 build:
+ * star[3][33] | nApNm1[4][135] | E[162] | w[M] | W[M]; neigh_int = nAmNm1[4][135] | w[M]
+ * (src/Initializer/Typedefs.h:187-210, src/Equations/viscoelastic2/Model/IntegrationData.h).
+ *
+ * ssb_visco_ader  replaces linearckanelastic Spacetime::computeBatchedAder (src/Kernels/LinearCKAnelastic/Time.cpp:122-190,
+ *                 per-cell computeAder :50-120);
+ * ssb_visco_local replaces Local::computeBatchedIntegral (src/Kernels/LinearCKAnelastic/Local.cpp:112-250, per-cell :63-110);
+ * ssb_visco_neigh replaces Neighbor::computeBatchedNeighborsIntegral (src/Kernels/LinearCKAnelastic/Neighbor.cpp:162-260,
+ *                 per-cell :71-130); regular faces only in this revision (DR faces are skipped). */
+int ssb_visco_ader(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
+                   ssb_array_t local_int, const double* coeffs, long long n, void* stream);
+int ssb_visco_local(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
+                    ssb_array_t local_int, const uint8_t* face_types, long long n, void* stream);
+int ssb_visco_neigh(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, const void* const* nb_ptrs,
+                    const long long* nb_idx, ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types,
+                    const uint8_t* face_rel, long long n, const int* perm, void* stream);
+
 const char* ssb_error_string(int code);
 const char* ssb_version(void);
 

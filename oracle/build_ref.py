@@ -85,8 +85,10 @@ def compile_cfg(ref, cfg, force=False):
     procs = []
     t0 = time.time()
     rs_flags = [f"-I{os.path.join(HERE, 'stub')}", f"-I{os.path.join(ref, 'src')}"]
-    for src in [os.path.join(sub, "kernel.cpp"), os.path.join(sub, "init.cpp"),
-                os.path.join(sub, "tensor.cpp"), harness, os.path.join(HERE, "ref_rs.cpp")]:
+    sources = [os.path.join(sub, "kernel.cpp"), os.path.join(sub, "init.cpp"), os.path.join(sub, "tensor.cpp"), harness]
+    if eq != "viscoelastic2":
+        sources.append(os.path.join(HERE, "ref_rs.cpp"))
+    for src in sources:
         obj = os.path.join(REFDIR, "gen", cfg, os.path.basename(src) + ".o")
         objs.append(obj)
         extra = rs_flags if src.endswith("ref_rs.cpp") else []

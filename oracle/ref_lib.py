@@ -177,3 +177,91 @@ class RefLib:
 
     def threads(self):
         return int(self.lib.ssref_threads())
+
+
+class ViscoRefLib:
+    """The reference's generated viscoelastic2 kernels (oracle/ref_harness_visco.cpp).  Arrays cross in the
+    logical layout of oracle/visco.py; conversion to the reference's padded column-major layout happens here."""
+
+    def __init__(self, cfg):
+        path = os.path.join(HERE, "_ref", f"libssref_{cfg}.so")
+        self.lib = ctypes.CDLL(path)
+        info = np.zeros(12, dtype=np.int64)
+        self.lib.ssrefv_info(_p(info))
+        (self.order, size, self.qsize, self.qanesize, self.qextsize, self.B, self.ld, self.starsize, self.asize,
+         self.esize, self.wsize, self.Wsize) = [int(x) for x in info]
+        self.dtype = np.float32 if size == 4 else np.float64
+        self.mech = self.wsize
+        self.lib.ssrefv_proxy_all.restype = ctypes.c_double
+        assert self.starsize == 33 and self.asize == 135 and self.Wsize == self.mech
+
+    def to_ref(self, x):
+        return O.to_ref_layout(np.ascontiguousarray(x, dtype=self.dtype), self.ld)
+
+    def from_ref(self, x):
+        return O.from_ref_layout(x, self.B, self.ld)
+
+    def ane_to_ref(self, x):
+        """[n, B, 6, M] -> [n, M*6*ld] with index k + ld (p + 6 m)."""
+        n, b, p, m = x.shape
+        out = np.zeros((n, m, p, self.ld), dtype=self.dtype)
+        out[:, :, :, :b] = x.transpose(0, 3, 2, 1)
+        return out.reshape(n, -1)
+
+    def ane_from_ref(self, x):
+        n = x.shape[0]
+        return np.ascontiguousarray(x.reshape(n, self.mech, 6, self.ld)[:, :, :, :self.B].transpose(0, 3, 2, 1))
+
+    def flops(self):
+        nz = np.zeros(56, dtype=np.int64)
+        self.lib.ssrefv_flops(_p(nz))
+        return {"derivative": int(nz[0]), "volumeExt": int(nz[1]), "localFluxExt": [int(v) for v in nz[2:6]],
+                "local": int(nz[6]), "neighborFluxExt": [int(v) for v in nz[7:55]], "neighbor": int(nz[55])}
+
+    def _c(self, x):
+        return np.ascontiguousarray(x, dtype=self.dtype)
+
+    def ader(self, Q, Qane, star, E, w, W, coeffs):
+        n = Q.shape[0]
+        q, qa = self.to_ref(Q), self.ane_to_ref(Qane)
+        I = np.zeros_like(q)
+        Ia = np.zeros_like(qa)
+        c = self._c(coeffs)
+        self.lib.ssrefv_ader(ctypes.c_int64(n), _p(c), _p(q), _p(qa), _p(self._c(star)), _p(self._c(E)), _p(self._c(w)),
+                             _p(self._c(W)), _p(I), _p(Ia))
+        return self.from_ref(I), self.ane_from_ref(Ia)
+
+    def local(self, Q, Qane, I, Iane, star, Aplus, E, w, W, face_types):
+        n = Q.shape[0]
+        q, qa = self.to_ref(Q), self.ane_to_ref(Qane)
+        ft = np.ascontiguousarray(face_types, dtype=np.uint8)
+        self.lib.ssrefv_local(ctypes.c_int64(n), _p(q), _p(qa), _p(self.to_ref(I)), _p(self.ane_to_ref(Iane)),
+                              _p(self._c(star)), _p(self._c(Aplus)), _p(self._c(E)), _p(self._c(w)), _p(self._c(W)), _p(ft))
+        return self.from_ref(q), self.ane_from_ref(qa)
+
+    def neigh(self, Q, Qane, Iall, neighbors, Aminus, w, face_rel, face_types):
+        n = Q.shape[0]
+        q, qa = self.to_ref(Q), self.ane_to_ref(Qane)
+        nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+        fr = np.ascontiguousarray(face_rel, dtype=np.uint8)
+        ft = np.ascontiguousarray(face_types, dtype=np.uint8)
+        self.lib.ssrefv_neigh(ctypes.c_int64(n), _p(q), _p(qa), _p(self.to_ref(Iall)), _p(nb), _p(self._c(Aminus)),
+                              _p(self._c(w)), _p(fr), _p(ft))
+        return self.from_ref(q), self.ane_from_ref(qa)
+
+    def threads(self):
+        return os.cpu_count() or 1
+
+    def proxy_all(self, d, coeffs, passes):
+        """Proxy `all` on the host cores; returns (seconds, Q, Qane)."""
+        n = d["Q"].shape[0]
+        q, qa = self.to_ref(d["Q"]), self.ane_to_ref(d["Qane"])
+        I = np.zeros_like(q)
+        Ia = np.zeros_like(qa)
+        c = self._c(coeffs)
+        t = self.lib.ssrefv_proxy_all(
+            ctypes.c_int64(n), ctypes.c_int(passes), _p(c), _p(q), _p(qa), _p(I), _p(Ia), _p(self._c(d["star"])),
+            _p(self._c(d["Aplus"])), _p(self._c(d["Aminus"])), _p(self._c(d["E"])), _p(self._c(d["w"])), _p(self._c(d["W"])),
+            _p(np.ascontiguousarray(d["neighbors"], dtype=np.int64)), _p(np.ascontiguousarray(d["face_rel"], dtype=np.uint8)),
+            _p(np.ascontiguousarray(d["face_types"], dtype=np.uint8)))
+        return float(t), self.from_ref(q), self.ane_from_ref(qa)

@@ -17,6 +17,7 @@ SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",
     "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_neigh",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
+    "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh",
     "ssb_error_string", "ssb_version",
 ]
 
@@ -83,6 +84,9 @@ def load_library():
     lib.ssb_friction_lsw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
     lib.ssb_friction_rsfvw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
     lib.ssb_neigh_dr.argtypes = [P, A, P, P, P, P, LL, P]
+    lib.ssb_visco_ader.argtypes = [P, A, A, A, A, A, P, LL, P]
+    lib.ssb_visco_local.argtypes = [P, A, A, A, A, A, P, LL, P]
+    lib.ssb_visco_neigh.argtypes = [P, A, A, P, P, A, A, P, P, LL, P, P]
     _lib = lib
     return lib
 
@@ -174,6 +178,20 @@ class Context:
               perm=None, stream=None):
         _check(self.lib.ssb_neigh(self.handle, dofs, _ptr(nb_ptrs), _ptr(nb_idx), idofs, neigh_int,
                                   _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
+
+    # -- viscoelastic2 --------------------------------------------------------------------------
+    def visco_ader(self, dofs, dofs_ane, idofs, idofs_ane, local_int, coeffs, n, stream=None):
+        keep, c = self._coeffs(coeffs)
+        _check(self.lib.ssb_visco_ader(self.handle, dofs, dofs_ane, idofs, idofs_ane, local_int, c, n, _stream(stream)))
+
+    def visco_local(self, dofs, dofs_ane, idofs, idofs_ane, local_int, face_types, n, stream=None):
+        _check(self.lib.ssb_visco_local(self.handle, dofs, dofs_ane, idofs, idofs_ane, local_int, _ptr(face_types), n,
+                                        _stream(stream)))
+
+    def visco_neigh(self, dofs, dofs_ane, idofs, neigh_int, face_types, face_rel, n, nb_idx=None, nb_ptrs=None,
+                    perm=None, stream=None):
+        _check(self.lib.ssb_visco_neigh(self.handle, dofs, dofs_ane, _ptr(nb_ptrs), _ptr(nb_idx), idofs, neigh_int,
+                                        _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
 
     # -- dynamic rupture ------------------------------------------------------------------------
     def dr_interp(self, der_plus, der_minus, tinv_t, face_info, q_plus, q_minus, coeffs, n, perm=None, stream=None):

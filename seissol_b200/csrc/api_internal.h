@@ -6,6 +6,7 @@
 
 #include "kernels_elastic.cuh"
 #include "kernels_dr.cuh"
+#include "kernels_visco.cuh"
 
 namespace ssb {
 
@@ -30,6 +31,19 @@ struct DrKernelSet {
   int (*friction)(const FrictionParams&, int law, cudaStream_t);
   int (*neighDr)(const NeighDrParams&, cudaStream_t);
 };
+
+struct ViscoKernelSet {
+  int order;
+  int realSize;
+  int B;
+  int BP;
+  int elemsPerCta;
+  int (*ader)(const ViscoLocalParams&, cudaStream_t);
+  int (*local)(const ViscoLocalParams&, cudaStream_t);
+  int (*neigh)(const ViscoNeighParams&, cudaStream_t);
+};
+const ViscoKernelSet* viscokernelset_o5_f32();
+const ViscoKernelSet* viscokernelset_o5_f64();
 
 const DrKernelSet* drkernelset_o4_f32();
 const DrKernelSet* drkernelset_o5_f32();

@@ -17,6 +17,7 @@ struct ssb_ctx {
   const KernelSet* ksLocal;  // volume + local flux (with or without the predictor)
   const KernelSet* ksNeigh;
   const DrKernelSet* dr;
+  const ViscoKernelSet* visco;
   int ppad;
   int order;
   int realSize;
@@ -178,7 +179,17 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
     return SSB_EINVAL;
   }
   *out = nullptr;
-  if (equation != 0 || mechanisms != 0) {
+  const ViscoKernelSet* visco = nullptr;
+  if (equation == 1) {
+    // viscoelastic2: order 5 with 3 mechanisms is the compiled configuration (BASELINE.json configs[2])
+    if (mechanisms != kVM || order != 5) {
+      return SSB_EUNSUPPORTED;
+    }
+    visco = real_size == 4 ? viscokernelset_o5_f32() : (real_size == 8 ? viscokernelset_o5_f64() : nullptr);
+    if (visco == nullptr) {
+      return SSB_EUNSUPPORTED;
+    }
+  } else if (equation != 0 || mechanisms != 0) {
     return SSB_EUNSUPPORTED;
   }
   const KernelSet* ks = lookup(order, real_size);
@@ -203,7 +214,8 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
   if (forced == 3 || (forced == 4 && ks4 != nullptr)) {
     c->ks = c->ksAder = c->ksLocal = c->ksNeigh = forced == 4 ? ks4 : ks;
   }
-  c->dr = lookupDr(order, real_size);
+  c->visco = visco;
+  c->dr = visco != nullptr ? nullptr : lookupDr(order, real_size);
   c->ppad = c->dr != nullptr ? c->dr->PP : 0;
   c->order = order;
   c->realSize = real_size;
@@ -495,6 +507,86 @@ int ssb_neigh_dr(ssb_ctx* c, ssb_array_t dofs, const void* const* godunov, const
   p.ldg = c->ldq;
   p.ppad = c->ppad;
   return c->dr->neighDr(p, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int fillVisco(ssb_ctx* c, ViscoLocalParams& p, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs,
+              ssb_array_t idofs_ane, ssb_array_t local_int, const uint8_t* face_types, const double* coeffs, long long n) {
+  if (c == nullptr || c->visco == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  std::memset(&p, 0, sizeof(p));
+  if (n == 0) {
+    return 0;
+  }
+  p.dofs = conv(dofs);
+  p.dofsAne = conv(dofs_ane);
+  p.idofs = conv(idofs);
+  p.idofsAne = conv(idofs_ane);
+  p.localInt = conv(local_int);
+  if (!p.dofs.present() || !p.dofsAne.present() || !p.idofs.present() || !p.idofsAne.present() || !p.localInt.present()) {
+    return SSB_EINVAL;
+  }
+  p.faceTypes = face_types;
+  p.n = n;
+  p.ldg = c->ldq;
+  for (int d = 0; d < c->order; ++d) {
+    p.coeffs[d] = coeffs != nullptr ? coeffs[d] : 0.0;
+  }
+  return 0;
+}
+}  // namespace
+
+int ssb_visco_ader(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
+                   ssb_array_t local_int, const double* coeffs, long long n, void* stream) {
+  if (coeffs == nullptr) {
+    return SSB_EINVAL;
+  }
+  ViscoLocalParams p;
+  const int rc = fillVisco(c, p, dofs, dofs_ane, idofs, idofs_ane, local_int, nullptr, coeffs, n);
+  if (rc != 0 || n == 0) {
+    return rc;
+  }
+  return c->visco->ader(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_visco_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
+                    ssb_array_t local_int, const uint8_t* face_types, long long n, void* stream) {
+  ViscoLocalParams p;
+  const int rc = fillVisco(c, p, dofs, dofs_ane, idofs, idofs_ane, local_int, face_types, nullptr, n);
+  if (rc != 0 || n == 0) {
+    return rc;
+  }
+  return c->visco->local(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_visco_neigh(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, const void* const* nb_ptrs,
+                    const long long* nb_idx, ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types,
+                    const uint8_t* face_rel, long long n, const int* perm, void* stream) {
+  if (c == nullptr || c->visco == nullptr || n < 0 || face_rel == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  ViscoNeighParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  p.dofsAne = conv(dofs_ane);
+  p.idofs = conv(idofs);
+  p.neighInt = conv(neigh_int);
+  p.nbPtrs = nb_ptrs;
+  p.nbIdx = nb_idx;
+  if (!p.dofs.present() || !p.dofsAne.present() || !p.neighInt.present() ||
+      (nb_ptrs == nullptr && (nb_idx == nullptr || !p.idofs.present()))) {
+    return SSB_EINVAL;
+  }
+  p.faceTypes = face_types;
+  p.faceRel = face_rel;
+  p.perm = perm;
+  p.n = n;
+  p.ldg = c->ldq;
+  return c->visco->neigh(p, static_cast<cudaStream_t>(stream));
 }
 
 const char* ssb_error_string(int code) {

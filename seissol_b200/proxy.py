@@ -357,3 +357,155 @@ class DrProxyKernels(ProxyKernels):
         self.local(stream)
         self.godunov_dr(stream)
         self.neigh_dr(stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# viscoelastic2 (anelastic attenuation, 3 mechanisms, order 5; BASELINE.json configs[2])
+VISCO_FLOPS = {"derivative": 120489, "volumeExt": 15924, "localFluxExt": 12708 + 12780 + 22068 + 20124, "local": 14175,
+               "neighborFluxExt": 4 * 17511.0, "neighbor": 1575}   # kernel::X::NonZeroFlops of the generated kernels
+
+
+def visco_nz_flops_per_element(kernel):
+    f = VISCO_FLOPS
+    ader = f["derivative"]
+    lwo = f["volumeExt"] + f["localFluxExt"] + f["local"]
+    neigh = f["neighborFluxExt"] + f["neighbor"]
+    return {"ader": ader, "localwoader": lwo, "local": ader + lwo, "neigh": neigh, "all": ader + lwo + neigh}[kernel]
+
+
+def visco_algorithmic_bytes_per_element(real_size, kernel, mech=3):
+    """SURVEY.md §8(d), unpadded reals: Q 315, Qane 630, star 99, E/w/W 168, A 4 x 135."""
+    q, qa, s, ew, a = 315, 210 * mech, 99, 54 * mech + 2 * mech, 135
+    reals = {"ader": 2 * q + 2 * qa + s + ew, "localwoader": 3 * q + 3 * qa + s + ew + 4 * a,
+             "local": 3 * q + 3 * qa + s + ew + 4 * a, "neigh": 4 * q + 2 * (q + qa) + 4 * a + mech}
+    reals["all"] = reals["ader"] + reals["localwoader"] + reals["neigh"]
+    return reals[kernel] * real_size
+
+
+class ViscoProxyData:
+    """Fake single-layer storage of the viscoelastic2 proxy.  Device layout: dofs/buffers [n, 9*ld]; dofs_ane/buffers_ane
+    [n, 18*ld] (column p + 6 m); local_int [n, 807] = star[3][33] | nApNm1[4][135] | E[162] | w[3] | W[3];
+    neigh_int [n, 543] = nAmNm1[4][135] | w[3]."""
+
+    MECH = 3
+
+    def __init__(self, ctx, cells, device="cuda:0"):
+        import torch
+        self.torch, self.ctx, self.cells = torch, ctx, cells
+        self.device = torch.device(device)
+        self.dtype = torch.float32 if ctx.real_size == 4 else torch.float64
+        self.np_dtype = np.float32 if ctx.real_size == 4 else np.float64
+        self.perm = None
+
+    @classmethod
+    def from_host(cls, ctx, d, device="cuda:0"):
+        """d: dict in the logical layout of oracle/visco.py::proxy_data."""
+        self = cls(ctx, d["Q"].shape[0], device)
+        t, n = self.torch, self.cells
+        self.dofs = self.q_to_device(d["Q"])
+        self.dofs_ane = self.ane_to_device(d["Qane"])
+        self.buffers = self.q_to_device(d["I"]) if "I" in d else t.zeros_like(self.dofs)
+        self.buffers_ane = self.ane_to_device(d["Iane"]) if "Iane" in d else t.zeros_like(self.dofs_ane)
+        li = np.concatenate([d["star"].reshape(n, 99), d["Aplus"].reshape(n, 540), d["E"].reshape(n, 162),
+                             d["w"].reshape(n, 3), d["W"].reshape(n, 3)], axis=1)
+        ni = np.concatenate([d["Aminus"].reshape(n, 540), d["w"].reshape(n, 3)], axis=1)
+        self.local_int = t.from_numpy(np.ascontiguousarray(li, dtype=self.np_dtype)).to(self.device)
+        self.neigh_int = t.from_numpy(np.ascontiguousarray(ni, dtype=self.np_dtype)).to(self.device)
+        self.face_rel = t.from_numpy(np.ascontiguousarray(d["face_rel"], dtype=np.uint8)).to(self.device)
+        self.face_types = t.from_numpy(np.ascontiguousarray(d["face_types"], dtype=np.uint8)).to(self.device)
+        self.neighbors = t.from_numpy(np.ascontiguousarray(d["neighbors"], dtype=np.int64)).to(self.device)
+        return self
+
+    @classmethod
+    def synthetic(cls, ctx, cells, device="cuda:0", seed=42, scale=1e-2):
+        self = cls(ctx, cells, device)
+        t = self.torch
+        g = t.Generator(device=self.device)
+        g.manual_seed(seed)
+        ld, B = ctx.ld, ctx.B
+
+        def modal(cols):
+            x = t.rand((cells, cols, ld), generator=g, device=self.device, dtype=self.dtype) * 2 - 1
+            if ld > B:
+                x[:, :, B:] = 0
+            return x.reshape(cells, cols * ld).contiguous()
+
+        self.dofs, self.dofs_ane = modal(9), modal(18)
+        self.buffers, self.buffers_ane = t.zeros_like(self.dofs), t.zeros_like(self.dofs_ane)
+        self.local_int = ((t.rand((cells, 807), generator=g, device=self.device, dtype=self.dtype) * 2 - 1) * scale).contiguous()
+        self.neigh_int = ((t.rand((cells, 543), generator=g, device=self.device, dtype=self.dtype) * 2 - 1) * scale).contiguous()
+        rel = t.empty((cells, 4, 2), dtype=t.uint8, device=self.device)
+        rel[:, :, 0] = t.randint(0, 4, (cells, 4), generator=g, device=self.device).to(t.uint8)
+        rel[:, :, 1] = t.randint(0, 3, (cells, 4), generator=g, device=self.device).to(t.uint8)
+        self.face_rel = rel.contiguous()
+        self.face_types = t.zeros((cells, 4), dtype=t.uint8, device=self.device)
+        self.neighbors = t.randint(0, cells, (cells, 4), generator=g, device=self.device, dtype=t.int64)
+        return self
+
+    def q_to_device(self, x):
+        n, b, q = x.shape
+        out = np.zeros((n, q, self.ctx.ld), dtype=self.np_dtype)
+        out[:, :, :b] = x.transpose(0, 2, 1)
+        return self.torch.from_numpy(out.reshape(n, q * self.ctx.ld)).to(self.device)
+
+    def ane_to_device(self, x):
+        n, b, p, m = x.shape
+        out = np.zeros((n, m, p, self.ctx.ld), dtype=self.np_dtype)
+        out[:, :, :, :b] = x.transpose(0, 3, 2, 1)
+        return self.torch.from_numpy(out.reshape(n, m * p * self.ctx.ld)).to(self.device)
+
+    def q_to_logical(self, t):
+        x = t.detach().cpu().numpy().reshape(t.shape[0], 9, self.ctx.ld)
+        return np.ascontiguousarray(x[:, :, :self.ctx.B].transpose(0, 2, 1))
+
+    def ane_to_logical(self, t):
+        x = t.detach().cpu().numpy().reshape(t.shape[0], self.MECH, 6, self.ctx.ld)
+        return np.ascontiguousarray(x[:, :, :, :self.ctx.B].transpose(0, 3, 2, 1))
+
+    def sort_by_face_relation(self):
+        t = self.torch
+        j = self.face_rel[:, :, 0].to(t.int64)
+        h = self.face_rel[:, :, 1].to(t.int64)
+        key = (j[:, 0] + 4 * j[:, 1] + 16 * j[:, 2] + 64 * j[:, 3]) * 81 + h[:, 0] + 3 * h[:, 1] + 9 * h[:, 2] + 27 * h[:, 3]
+        self.perm = t.argsort(key, stable=True).to(t.int32).contiguous()
+        return self.perm
+
+    def bytes_resident(self):
+        return sum(x.numel() * x.element_size() for x in
+                   (self.dofs, self.dofs_ane, self.buffers, self.buffers_ane, self.local_int, self.neigh_int,
+                    self.face_rel, self.face_types, self.neighbors))
+
+
+class ViscoProxyKernels:
+    """Proxy kernel names on the viscoelastic2 context (src/Proxy/KernelDevice.cpp with the LinearCKAnelastic kernels)."""
+
+    def __init__(self, ctx, data):
+        self.ctx, self.d = ctx, data
+        self.coeffs = integrate_coeffs(ctx.order, 0.0, TIMESTEP)
+
+    def ader(self, stream=None):
+        d = self.d
+        self.ctx.visco_ader(api.strided(d.dofs), api.strided(d.dofs_ane), api.strided(d.buffers), api.strided(d.buffers_ane),
+                            api.strided(d.local_int), self.coeffs, d.cells, stream=stream)
+
+    def localwoader(self, stream=None):
+        d = self.d
+        self.ctx.visco_local(api.strided(d.dofs), api.strided(d.dofs_ane), api.strided(d.buffers), api.strided(d.buffers_ane),
+                             api.strided(d.local_int), d.face_types, d.cells, stream=stream)
+
+    def local(self, stream=None):
+        self.ader(stream)
+        self.localwoader(stream)
+
+    def neigh(self, stream=None):
+        d = self.d
+        self.ctx.visco_neigh(api.strided(d.dofs), api.strided(d.dofs_ane), api.strided(d.buffers), api.strided(d.neigh_int),
+                             d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
+
+    def all(self, stream=None):
+        self.local(stream)
+        self.neigh(stream)
+
+    def run(self, name, stream=None):
+        for part in name.split(","):
+            getattr(self, part)(stream)

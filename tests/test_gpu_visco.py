@@ -1,0 +1,108 @@
+"""GPU parity tests (-m gpu) of the viscoelastic2 kernels, through the C ABI, against the numpy oracle
+(oracle/visco.py, pinned against the reference's generated kernels) and the committed golden vectors.
+Tolerances: BASELINE.json's bar for DOFs after N steps is 1e-5 (single) / 1e-11 (double) relative L2; single kernels
+are held to 2e-6 / 5e-15."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import aderdg as O
+from oracle import visco as V
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def tol(dt):
+    return 2e-6 if dt == np.float32 else 5e-15
+
+
+@pytest.fixture(scope="module")
+def gpu(built_library):
+    import torch
+    from seissol_b200 import api, proxy
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch, api, proxy
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 13, 200])
+def test_visco_kernels_match_oracle(gpu, dt, n):
+    torch, api, proxy = gpu
+    ctx = api.Context(5, np.dtype(dt).itemsize, equation=1, mechanisms=3)
+    tab = O.load_tables(5, dt)
+    d = V.proxy_data(5, n, dt, seed=100 + n)
+    d["face_types"][::5, 1] = 3
+    d["face_types"][::7, 2] = 5
+    coeffs = O.time_integrate_coeffs(5, 0.0, 1.0, dt)
+    star, E = V.star_dense(d["star"]), V.e_dense(d["E"], 3)
+    data = proxy.ViscoProxyData.from_host(ctx, d)
+    k = proxy.ViscoProxyKernels(ctx, data)
+    k.ader()
+    torch.cuda.synchronize()
+    I, Ia = V.ader(tab, d["Q"], d["Qane"], star, E, d["w"], d["W"], coeffs)
+    assert rel_l2(data.q_to_logical(data.buffers), I) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.buffers_ane), Ia) < tol(dt)
+    k.localwoader()
+    torch.cuda.synchronize()
+    ql, qal = V.local(tab, d["Q"], d["Qane"], I, Ia, star, V.flux_dense(d["Aplus"]), E, d["w"], d["W"], d["face_types"])
+    assert rel_l2(data.q_to_logical(data.dofs), ql) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), qal) < tol(dt)
+    assert rel_l2(data.q_to_logical(data.dofs) - d["Q"], ql - d["Q"]) < 50 * tol(dt)
+    data.sort_by_face_relation()
+    k.neigh()
+    torch.cuda.synchronize()
+    qn, qan = V.neighbor(tab, ql, qal, I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"], d["face_types"])
+    assert rel_l2(data.q_to_logical(data.dofs), qn) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), qan) < tol(dt)
+    assert rel_l2(data.q_to_logical(data.dofs) - ql, qn - ql) < 50 * tol(dt)
+
+
+@pytest.mark.parametrize("cfg,dt", [("visco_o5_f32", np.float32), ("visco_o5_f64", np.float64)])
+def test_visco_matches_reference_golden(gpu, cfg, dt):
+    torch, api, proxy = gpu
+    g = dict(np.load(os.path.join(GOLDEN, f"{cfg}.npz")))
+    ctx = api.Context(5, np.dtype(dt).itemsize, equation=1, mechanisms=3)
+    data = proxy.ViscoProxyData.from_host(ctx, g)
+    k = proxy.ViscoProxyKernels(ctx, data)
+    k.coeffs = g["coeffs"]
+    k.ader()
+    k.localwoader()
+    torch.cuda.synchronize()
+    assert rel_l2(data.q_to_logical(data.buffers), g["I"]) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.buffers_ane), g["Iane"]) < tol(dt)
+    assert rel_l2(data.q_to_logical(data.dofs), g["Q_local"]) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), g["Qane_local"]) < tol(dt)
+    k.neigh()
+    torch.cuda.synchronize()
+    assert rel_l2(data.q_to_logical(data.dofs), g["Q_all"]) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), g["Qane_all"]) < tol(dt)
+
+
+@pytest.mark.parametrize("dt,bar", [(np.float32, 1e-5), (np.float64, 1e-11)])
+def test_visco_all_ten_steps(gpu, dt, bar):
+    """BASELINE.json north_star: DOFs after N time steps within 1e-5 (single) / 1e-11 (double) relative L2."""
+    torch, api, proxy = gpu
+    ctx = api.Context(5, np.dtype(dt).itemsize, equation=1, mechanisms=3)
+    tab = O.load_tables(5, dt)
+    d = V.proxy_data(5, 300, dt, seed=9)
+    coeffs = O.time_integrate_coeffs(5, 0.0, 1.0, dt)
+    data = proxy.ViscoProxyData.from_host(ctx, d)
+    data.sort_by_face_relation()
+    k = proxy.ViscoProxyKernels(ctx, data)
+    for _ in range(10):
+        k.all()
+        d = V.proxy_step(tab, d, coeffs, "all")
+    torch.cuda.synchronize()
+    assert rel_l2(data.q_to_logical(data.dofs), d["Q"]) < bar
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), d["Qane"]) < bar
+
+
+def test_visco_context_rejects_unsupported():
+    from seissol_b200 import api
+    with pytest.raises(api.SsbError):
+        api.Context(6, 4, equation=1, mechanisms=3)
+    with pytest.raises(api.SsbError):
+        api.Context(5, 4, equation=1, mechanisms=2)

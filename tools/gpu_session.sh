@@ -22,6 +22,10 @@ v4)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v4.txt 2>&1
   [ -f $NP7 ] && SSB_LIB=$NP7 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v4_np7.txt 2>&1
   SSB_KGEN=3 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64_v3.txt 2>&1 ;;
+visco)
+  timeout 900 python -m pytest tests/test_gpu_visco.py -m gpu -x -q > $out/pytest_visco.log 2>&1; echo "exit $?" >> $out/pytest_visco.log
+  timeout 300 python tools/quick_bench_visco.py > $out/qb_visco.txt 2>&1
+  timeout 300 python tools/quick_bench_visco.py --real 8 --cells 500000 > $out/qb_visco_f64.txt 2>&1 ;;
 qbf64)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 part)
