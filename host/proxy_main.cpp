@@ -1,0 +1,249 @@
+// ssb_proxy: C++ host of the SeisSol proxy on the B200-native kernels.
+//
+//   ssb_proxy <cells> <timesteps> <kernel[,kernel...]> [-f plain|json] [--order N] [--precision s|d] [--dump PREFIX]
+//
+// Same command line, kernel names, composition, timing protocol and output as the reference proxy
+// (app/Proxy/Main.cpp, src/Proxy/{Common,Runner,Allocator,KernelDevice}.cpp): one untimed warm-up pass, then `timesteps`
+// timed passes between two stream synchronisations; `all` = local then neigh, `local` = ader then localwoader.
+// Fake data as fakeData (src/Proxy/Allocator.cpp:49-134): per cell and face (side U{0..3}, orientation U{0..2},
+// neighbor U{0..cells-1}) drawn from std::mt19937(cells) in the reference's order; values are bounded
+// instead of fillWithStuff.  --dump writes the inputs and the final DOFs as raw arrays for the parity test
+// (tests/test_gpu_host_cpp.py).  Elastic kernels only: all, local, neigh, ader, localwoader.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "ssb_host.hpp"
+
+using namespace seissol_b200;
+
+namespace {
+
+enum class Kernel { All, Local, Neighbor, Ader, LocalWOAder };
+
+bool str2kernel(const std::string& s, std::vector<Kernel>& out) {
+  std::stringstream ss(s);
+  std::string part;
+  while (std::getline(ss, part, ',')) {
+    if (part == "all") out.push_back(Kernel::All);
+    else if (part == "local") out.push_back(Kernel::Local);
+    else if (part == "neigh") out.push_back(Kernel::Neighbor);
+    else if (part == "ader") out.push_back(Kernel::Ader);
+    else if (part == "localwoader") out.push_back(Kernel::LocalWOAder);
+    else {
+      std::cerr << "Unknown kernel string: " << part << std::endl;
+      return false;
+    }
+  }
+  return !out.empty();
+}
+
+// static flop counts of the reference's generated kernels (kernel::X::NonZeroFlops / HardwareFlops; neighboringFlux:
+// mean over the 48 relations), elastic, per order
+struct Flops { double derNz, derHw, volNz, volHw, lfNz, lfHw, nfNz, nfHw; };
+Flops flopsOf(int order) {
+  switch (order) {
+    case 4: return {6642, 34146, 4806, 19584, 18972, 0, 4 * 5073.0, 0};
+    case 6: return {56286, 248292, 34839, 127872, 79200, 246528, 4 * 20805.0, 4 * 73728.0};
+    default: return {0, 0, 0, 0, 0, 0, 0, 0};
+  }
+}
+
+template <typename T>
+void upload(void*& dev, const std::vector<T>& host) {
+  checkCuda(cudaMalloc(&dev, host.size() * sizeof(T)), "cudaMalloc");
+  checkCuda(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy");
+}
+template <typename T>
+void dumpRaw(const std::string& path, const std::vector<T>& v) {
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+
+template <typename real>
+int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& kernels, const std::string& kernelStr, int order,
+        bool json, const std::string& dump) {
+  Context ctx(order, sizeof(real));
+  const int B = ctx.basisFunctions(), ld = ctx.leadingDimension();
+  const std::size_t qs = ctx.dofsSize();
+
+  // ---- fake data (Allocator.cpp:49-134)
+  std::mt19937 rng(static_cast<unsigned>(cells));
+  std::uniform_int_distribution<unsigned> sideDist(0, 3), orientationDist(0, 2);
+  std::uniform_int_distribution<std::size_t> cellDist(0, cells - 1);
+  std::vector<std::uint8_t> faceTypes(4 * cells, 0), faceRel(8 * cells);
+  std::vector<long long> neighbors(4 * cells);
+  for (std::size_t c = 0; c < cells; ++c) {
+    for (int f = 0; f < 4; ++f) {
+      faceRel[8 * c + 2 * f] = static_cast<std::uint8_t>(sideDist(rng));
+      faceRel[8 * c + 2 * f + 1] = static_cast<std::uint8_t>(orientationDist(rng));
+      neighbors[4 * c + f] = static_cast<long long>(cellDist(rng));
+    }
+  }
+  std::mt19937 vrng(42);
+  std::uniform_real_distribution<double> u(-1.0, 1.0);
+  const double scale = 1e-2;
+  std::vector<real> dofs(cells * qs, real(0)), buffers(cells * qs, real(0)), localInt(cells * 396), neighInt(cells * 324);
+  for (std::size_t c = 0; c < cells; ++c) {
+    for (int q = 0; q < 9; ++q) {
+      for (int k = 0; k < B; ++k) {
+        dofs[c * qs + q * ld + k] = static_cast<real>(u(vrng));
+      }
+    }
+  }
+  for (auto& v : localInt) v = static_cast<real>(u(vrng) * scale);
+  for (auto& v : neighInt) v = static_cast<real>(u(vrng) * scale);
+
+  Layer layer;
+  layer.size = cells;
+  layer.realSize = sizeof(real);
+  layer.dofsStride = qs;
+  upload(layer.dofs, dofs);
+  upload(layer.buffers, buffers);
+  upload(layer.localIntegration, localInt);
+  upload(layer.neighboringIntegration, neighInt);
+  void* p = nullptr;
+  upload(p, faceTypes); layer.faceTypes = static_cast<std::uint8_t*>(p);
+  upload(p, faceRel); layer.faceRelations = static_cast<std::uint8_t*>(p);
+  upload(p, neighbors); layer.faceNeighbors = static_cast<long long*>(p);
+
+  // processing order of the neighbor kernel: cells grouped by their four (neighbor face, orientation) pairs -- the
+  // reference's recorder groups by the same key (NeighIntegrationRecorder.cpp:142-144)
+  {
+    std::vector<std::pair<int, int>> keyed(cells);
+    for (std::size_t c = 0; c < cells; ++c) {
+      int kj = 0, kh = 0;
+      for (int f = 3; f >= 0; --f) {
+        kj = kj * 4 + faceRel[8 * c + 2 * f];
+        kh = kh * 3 + faceRel[8 * c + 2 * f + 1];
+      }
+      keyed[c] = {kj * 81 + kh, static_cast<int>(c)};
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<int> perm(cells);
+    for (std::size_t c = 0; c < cells; ++c) perm[c] = keyed[c].second;
+    upload(p, perm);
+    layer.permutation = static_cast<int*>(p);
+  }
+
+  kernels::Spacetime spacetime(ctx);
+  kernels::Local local(ctx);
+  kernels::Neighbor neighbor(ctx);
+  cudaStream_t stream;
+  checkCuda(cudaStreamCreate(&stream), "cudaStreamCreate");
+  const double dt = 1.0;  // src/Proxy/Constants.h
+  std::vector<double> coeffs(order);
+  double fact = 1.0;
+  for (int d = 0; d < order; ++d) {
+    fact *= (d + 1);
+    coeffs[d] = std::pow(dt, d + 1) / fact;  // MonomialBasis::integrate (src/Numerical/TimeBasis.h:82-96)
+  }
+  auto pass = [&]() {
+    for (Kernel k : kernels) {
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::Ader) spacetime.computeBatchedAder(coeffs.data(), dt, layer, stream);
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder) local.computeBatchedIntegral(layer, dt, stream);
+      if (k == Kernel::All || k == Kernel::Neighbor) neighbor.computeBatchedNeighborsIntegral(layer, stream);
+    }
+  };
+  pass();  // warm-up pass (Runner.cpp:93-95)
+  checkCuda(cudaStreamSynchronize(stream), "sync");
+  const auto t0 = std::chrono::steady_clock::now();
+  for (std::size_t t = 0; t < timesteps; ++t) {
+    pass();
+  }
+  checkCuda(cudaStreamSynchronize(stream), "sync");
+  const double time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  // ---- output (Runner.cpp:113-151, Common.cpp:91-151)
+  const Flops fl = flopsOf(order);
+  double nz = 0, hw = 0, reals = 0;
+  const double bq = double(B) * 9;
+  for (Kernel k : kernels) {
+    const bool a = k == Kernel::All || k == Kernel::Local || k == Kernel::Ader;
+    const bool l = k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder;
+    const bool n = k == Kernel::All || k == Kernel::Neighbor;
+    if (a) { nz += fl.derNz; hw += fl.derHw; reals += 2 * bq + 72; }
+    if (l) { nz += fl.volNz + fl.lfNz; hw += fl.volHw + fl.lfHw; reals += 3 * bq + 72 + 324; }
+    if (n) { nz += fl.nfNz; hw += fl.nfHw; reals += 6 * bq + 324; }
+  }
+  const double total = double(cells) * double(timesteps);
+  const double gnz = nz * total * 1e-9, ghw = hw * total * 1e-9, gib = reals * sizeof(real) * total / (1024.0 * 1024.0 * 1024.0);
+  if (!json) {
+    std::cout << "=================================================\n";
+    std::cout << "===            PERFORMANCE SUMMARY            ===\n";
+    std::cout << "=================================================\n";
+    std::cout << "seissol proxy mode                  : " << kernelStr << '\n';
+    std::cout << "time for seissol proxy              : " << time << '\n';
+    std::cout << "cycles                              : " << 0.0 << '\n' << '\n';
+    std::cout << "GFLOP (non-zero) for seissol proxy  : " << gnz << '\n';
+    std::cout << "GFLOP (hardware) for seissol proxy  : " << ghw << '\n';
+    std::cout << "GiB (estimate) for seissol proxy    : " << gib << '\n' << '\n';
+    std::cout << "GFLOPS (non-zero) for seissol proxy : " << gnz / time << '\n';
+    std::cout << "GFLOPS (hardware) for seissol proxy : " << ghw / time << '\n';
+    std::cout << "GiB/s (estimate) for seissol proxy  : " << gib / time << '\n';
+    std::cout << "element updates/s                   : " << total / time << '\n';
+    std::cout << "=================================================\n\n";
+  } else {
+    std::cout << "{\"name\":\"" << kernelStr << "\",\"time\":" << time << ",\"cycles\":0,\"gflop-nz\":" << gnz
+              << ",\"gflop-hw\":" << ghw << ",\"gib\":" << gib << ",\"gflops-nz\":" << gnz / time << ",\"gflops-hw\":" << ghw / time
+              << ",\"gibs\":" << gib / time << ",\"elem-updates-per-s\":" << total / time << "}\n";
+  }
+  if (!dump.empty()) {
+    std::vector<real> out(cells * qs);
+    checkCuda(cudaMemcpy(out.data(), layer.dofs, out.size() * sizeof(real), cudaMemcpyDeviceToHost), "cudaMemcpy");
+    dumpRaw(dump + "_Q0.bin", dofs);
+    dumpRaw(dump + "_Q.bin", out);
+    dumpRaw(dump + "_localInt.bin", localInt);
+    dumpRaw(dump + "_neighInt.bin", neighInt);
+    dumpRaw(dump + "_faceRel.bin", faceRel);
+    dumpRaw(dump + "_neighbors.bin", neighbors);
+    std::ofstream meta(dump + "_meta.txt");
+    meta << cells << ' ' << timesteps << ' ' << order << ' ' << sizeof(real) << ' ' << B << ' ' << ld << '\n';
+  }
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  std::vector<std::string> pos;
+  bool json = false;
+  int order = 6;
+  std::string precision = "s", dump;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if ((a == "-f" || a == "--format") && i + 1 < argc) json = std::string(argv[++i]) == "json";
+    else if (a == "--order" && i + 1 < argc) order = std::atoi(argv[++i]);
+    else if (a == "--precision" && i + 1 < argc) precision = argv[++i];
+    else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
+    else pos.push_back(a);
+  }
+  if (pos.size() != 3) {
+    std::cerr << "usage: ssb_proxy <cells> <timesteps> <kernel[,kernel]> [-f plain|json] [--order 4|5|6] [--precision s|d] "
+                 "[--dump PREFIX]\nkernels: all, local, neigh, ader, localwoader" << std::endl;
+    return -1;
+  }
+  std::vector<Kernel> kernels;
+  if (!str2kernel(pos[2], kernels)) {
+    return -1;
+  }
+  try {
+    const std::size_t cells = std::stoull(pos[0]), timesteps = std::stoull(pos[1]);
+    if (precision == "d") {
+      return run<double>(cells, timesteps, kernels, pos[2], order, json, dump);
+    }
+    return run<float>(cells, timesteps, kernels, pos[2], order, json, dump);
+  } catch (const std::exception& e) {
+    std::cerr << "ssb_proxy: " << e.what() << std::endl;
+    return 1;
+  }
+}

@@ -1,0 +1,154 @@
+// C++ host side of seissol_b200 above the C ABI (include/seissol_b200.h): the reference's batched kernel classes
+// with their names and argument meaning, bound to one `Layer` of device arrays instead of the recorder tables.
+//
+//   kernels::Spacetime::computeBatchedAder          <- src/Kernels/Spacetime.h:60-67, LinearCK/Time.cpp:142-217
+//   kernels::Time::evaluateBatched                  <- src/Kernels/Time.h:56-60,      LinearCK/Time.cpp:257-292
+//   kernels::Local::computeBatchedIntegral          <- src/Kernels/Local.h:64-68,     LinearCK/Local.cpp:255-395
+//   kernels::Neighbor::computeBatchedNeighborsIntegral <- src/Kernels/Neighbor.h:49-50, LinearCK/Neighbor.cpp:111-188
+//
+// Error behaviour follows the reference: device errors are fatal (`logError()` / APIWRAP abort) -> std::runtime_error.
+// There is no CPU path: constructing a Context without a CUDA device throws.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "seissol_b200.h"
+
+namespace seissol_b200 {
+
+inline void check(int rc, const char* what) {
+  if (rc != 0) {
+    throw std::runtime_error(std::string(what) + ": " + ssb_error_string(rc));
+  }
+}
+inline void checkCuda(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+  }
+}
+
+// One (ConvergenceOrder, real, equation) configuration (the reference builds one binary per configuration).
+class Context {
+  public:
+  Context(int order, int realSize, bool referenceLayout = false) : order_(order), realSize_(realSize) {
+    check(ssb_create(&ctx_, order, realSize, 0, 0), "ssb_create");
+    if (referenceLayout) {
+      check(ssb_layout_reference(ctx_), "ssb_layout_reference");
+    }
+    int q[24];
+    check(ssb_query(ctx_, q), "ssb_query");
+    basisFunctions_ = q[0];
+    ld_ = q[1];
+    dofsSize_ = q[2];
+    derivativesSize_ = q[3];
+  }
+  ~Context() { ssb_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  ssb_ctx* handle() const { return ctx_; }
+  int order() const { return order_; }
+  int realSize() const { return realSize_; }
+  int basisFunctions() const { return basisFunctions_; }
+  int leadingDimension() const { return ld_; }
+  std::size_t dofsSize() const { return dofsSize_; }             // reals per Q / I tensor
+  std::size_t derivativesSize() const { return derivativesSize_; }
+
+  private:
+  ssb_ctx* ctx_{nullptr};
+  int order_, realSize_, basisFunctions_{0}, ld_{0};
+  std::size_t dofsSize_{0}, derivativesSize_{0};
+};
+
+// Device arrays of one layer = the slice of the LTS storage one time cluster works on
+// (LTS::{Dofs, Buffers, Derivatives, LocalIntegration, NeighboringIntegration, CellInformation, FaceNeighbors},
+// src/Memory/Descriptor/LTS.h:97-119).  Arrays are contiguous per variable like Storage<Varmap> holds them.
+struct Layer {
+  std::size_t size{0};
+  int realSize{4};
+  void* dofs{nullptr};
+  void* buffers{nullptr};                 // time-integrated DOFs I
+  void* derivatives{nullptr};             // optional
+  void* localIntegration{nullptr};        // [size][396] star[3][24] | nApNm1[4][81]
+  void* neighboringIntegration{nullptr};  // [size][324] nAmNm1[4][81]
+  std::uint8_t* faceTypes{nullptr};       // [size][4]
+  std::uint8_t* faceRelations{nullptr};   // [size][4][2] {neighbor's face, orientation}
+  long long* faceNeighbors{nullptr};      // [size][4] index into buffers (proxy) ...
+  const void* const* faceNeighborPtrs{nullptr};  // ... or LTS::FaceNeighborsDevice pointers
+  int* permutation{nullptr};              // optional processing order of the neighbor kernel
+  std::size_t dofsStride{0}, derivativesStride{0};  // reals per cell
+};
+
+inline ssb_array_t strided(const void* base, std::size_t strideBytes) {
+  return ssb_array_t{nullptr, base, static_cast<long long>(strideBytes)};
+}
+inline ssb_array_t none() { return ssb_array_t{nullptr, nullptr, 0}; }
+
+namespace kernels {
+
+class Spacetime {
+  public:
+  explicit Spacetime(Context& ctx) : ctx_(ctx) {}
+  // coeffs: Taylor integration coefficients of [0, dt] (src/Numerical/TimeBasis.h:82-96), host array
+  void computeBatchedAder(const double* coeffs, double /*timeStepWidth*/, Layer& layer, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_ader(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), strided(layer.buffers, layer.dofsStride * rs),
+                   layer.derivatives != nullptr ? strided(layer.derivatives, layer.derivativesStride * rs) : none(),
+                   strided(layer.localIntegration, 396 * rs), coeffs, static_cast<long long>(layer.size), nullptr, stream),
+          "ssb_ader");
+  }
+
+  private:
+  Context& ctx_;
+};
+
+class Time {
+  public:
+  explicit Time(Context& ctx) : ctx_(ctx) {}
+  void evaluateBatched(const double* coeffs, const void* const* timeDerivatives, void* const* timeIntegratedDofs,
+                       std::size_t numElements, cudaStream_t stream) {
+    check(ssb_taylor(ctx_.handle(), ssb_array_t{timeDerivatives, nullptr, 0},
+                     ssb_array_t{const_cast<const void* const*>(timeIntegratedDofs), nullptr, 0}, coeffs,
+                     static_cast<long long>(numElements), stream),
+          "ssb_taylor");
+  }
+
+  private:
+  Context& ctx_;
+};
+
+class Local {
+  public:
+  explicit Local(Context& ctx) : ctx_(ctx) {}
+  void computeBatchedIntegral(Layer& layer, double /*timeStepWidth*/, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_local(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), strided(layer.buffers, layer.dofsStride * rs),
+                    strided(layer.localIntegration, 396 * rs), layer.faceTypes, static_cast<long long>(layer.size), nullptr,
+                    stream),
+          "ssb_local");
+  }
+
+  private:
+  Context& ctx_;
+};
+
+class Neighbor {
+  public:
+  explicit Neighbor(Context& ctx) : ctx_(ctx) {}
+  void computeBatchedNeighborsIntegral(Layer& layer, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_neigh(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), layer.faceNeighborPtrs, layer.faceNeighbors,
+                    strided(layer.buffers, layer.dofsStride * rs), strided(layer.neighboringIntegration, 324 * rs),
+                    layer.faceTypes, layer.faceRelations, static_cast<long long>(layer.size), layer.permutation, stream),
+          "ssb_neigh");
+  }
+
+  private:
+  Context& ctx_;
+};
+
+}  // namespace kernels
+}  // namespace seissol_b200

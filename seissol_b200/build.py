@@ -101,7 +101,29 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(f"[build] linked {lib}", flush=True)
+    if variant is None:
+        build_host(lib, verbose)
     return lib
+
+
+def build_host(lib, verbose=True):
+    """C++ host above the C ABI: host/ssb_host.hpp (the reference's batched kernel classes) + the proxy executable."""
+    root = os.path.join(HERE, "..")
+    src = os.path.join(root, "host", "proxy_main.cpp")
+    exe = os.path.join(LIBDIR, "ssb_proxy")
+    deps = [src, os.path.join(root, "host", "ssb_host.hpp"), os.path.join(root, "include", "seissol_b200.h"), lib]
+    if not _newer(exe, deps):
+        return exe
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O2", src, f"-I{os.path.join(root, 'include')}", f"-I{os.path.join(root, 'host')}",
+           f"-I{os.path.join(cuda, 'include')}", f"-L{LIBDIR}", "-lseissol_b200", f"-L{os.path.join(cuda, 'lib64')}",
+           "-lcudart", "-Wl,-rpath,$ORIGIN", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"host build failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"[build] built {exe}", flush=True)
+    return exe
 
 
 if __name__ == "__main__":
