@@ -34,6 +34,11 @@ REAL = 4
 KERNEL = "all"
 CELLS = 1_000_000
 CFG_NAME = {4: "elastic_o6_f32", 8: "elastic_o6_f64"}
+# DRAM bytes per element per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at
+# 296 000 elements, profiles/r1_v3b_ncu_summary_f32.txt): traffic ~ algorithmic bytes, i.e. no wasted re-reads
+NCU_DRAM_BYTES_PER_ELEMENT = {4: {"k_local<ader>": (0.715280e9 + 559.575552e6) / 296000,
+                                  "k_local<localwoader>": (1.663648e9 + 562.966016e6) / 296000,
+                                  "k_neigh": (3.397901e9 + 666.347008e6) / 296000}}
 FMA_PEAK = {4: 74.2, 8: 37.1}  # TFLOP/s, vector FMA, measured on this pool (tools/ubench/gen_ffma2.py); f64 = half rate
 
 
@@ -282,7 +287,11 @@ def run_ours(args):
                        "cells_per_gpu": args.cells, "l2": "inputs exceed L2 (%.1f GiB resident per GPU)" % (data.bytes_resident() / 2 ** 30),
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU", "finite": finite},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": (NCU_DRAM_BYTES_PER_ELEMENT[args.real][dom] * args.cells
+                                     if args.real in NCU_DRAM_BYTES_PER_ELEMENT else None),
+                         "traffic_note": "bytes per launch, scaled per element from the ncu --set full capture under profiles/",
+                         "algorithmic_bytes": dom_bytes * args.cells, "peak_kind": peak_kind,
                          "ms_per_launch": dom_ms,
                          "fp32_fma": {"achieved_tflops": dom_flops * args.cells / (dom_ms * 1e-3) / 1e12,
                                       "peak_tflops": FMA_PEAK[args.real], "frac": dom_flops * args.cells / (dom_ms * 1e-3) / 1e12 / FMA_PEAK[args.real],
@@ -340,7 +349,7 @@ def run_partitioned(args):
     nxl = max(2, int(round(args.cells / (5.0 * ny * nz))))
     nxl += nxl % 2 if (nxl * world) % 2 else 0
     nx = nxl * world
-    layout, data = D.build_partitioned(torch, dist, nx, ny, nz, rank, world, ctx.B, ctx.ld, dtype, device)
+    layout, data = D.build_partitioned(torch, dist, nx, ny, nz, rank, world, ctx.B, ctx.ld, dtype, device, scale=2e-3)
     data.sort_by_face_relation()
     coeffs = proxy.integrate_coeffs(ORDER, 0.0, proxy.TIMESTEP)
     backend = D.CudaBackend(ctx, data, coeffs)

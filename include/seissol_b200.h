@@ -85,6 +85,12 @@ int ssb_ader_local(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_array_
 int ssb_taylor(ssb_ctx* ctx, ssb_array_t derivs, ssb_array_t idofs, const double* coeffs,
                long long n, void* stream);
 
+/* LTS buffer accumulation: buffers = reset ? idofs : buffers + idofs, for cells whose neighbors in a larger time
+ * cluster read the sum over two sub-steps (LtsSetup::accumulateBuffers, src/Initializer/LtsSetup.h:21-111).  Replaces
+ * device.algorithms.streamBatchedData / accumulateBatchedData in TimeCluster::computeLocalIntegrationDevice
+ * (src/Solver/TimeStepping/TimeCluster.cpp:508-530). */
+int ssb_lts_accumulate(ssb_ctx* ctx, ssb_array_t buffers, ssb_array_t idofs, int reset, long long n, void* stream);
+
 /* Neighbor flux, all four faces and all 48 face relations in one launch.  Replaces
  * Neighbor::computeBatchedNeighborsIntegral (src/Kernels/LinearCK/Neighbor.cpp:111-188).
  * Neighbor data either as nb_ptrs (device [n][4] pointers to the neighbors' I,

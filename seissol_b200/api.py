@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(HERE, "lib", "libseissol_b2
 
 SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",
-    "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_neigh",
+    "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_lts_accumulate", "ssb_neigh",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh",
     "ssb_error_string", "ssb_version",
@@ -79,6 +79,7 @@ def load_library():
     lib.ssb_ader_local.argtypes = [P, A, A, A, A, P, P, LL, P, P]
     lib.ssb_taylor.argtypes = [P, A, A, P, LL, P]
     lib.ssb_neigh.argtypes = [P, A, P, P, A, A, P, P, LL, P, P]
+    lib.ssb_lts_accumulate.argtypes = [P, A, A, I, LL, P]
     lib.ssb_set_dr_layout.argtypes = [P, I]
     lib.ssb_dr_interp.argtypes = [P, A, A, P, P, P, P, P, LL, P, P]
     lib.ssb_friction_lsw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
@@ -173,6 +174,9 @@ class Context:
     def taylor(self, derivs, idofs, coeffs, n, stream=None):
         keep, c = self._coeffs(coeffs)
         _check(self.lib.ssb_taylor(self.handle, derivs, idofs, c, n, _stream(stream)))
+
+    def lts_accumulate(self, buffers, idofs, reset, n, stream=None):
+        _check(self.lib.ssb_lts_accumulate(self.handle, buffers, idofs, 1 if reset else 0, n, _stream(stream)))
 
     def neigh(self, dofs, idofs, neigh_int, face_types, face_rel, n, nb_idx=None, nb_ptrs=None,
               perm=None, stream=None):

@@ -20,6 +20,7 @@ struct KernelSet {
   int (*local)(const LocalParams&, bool ader, bool local, cudaStream_t);
   int (*neigh)(const NeighParams&, cudaStream_t);
   int (*taylor)(const TaylorParams&, cudaStream_t);
+  int (*accumulate)(const AccumulateParams&, cudaStream_t);
 };
 
 struct DrKernelSet {

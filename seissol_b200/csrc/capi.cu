@@ -344,6 +344,26 @@ int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* 
   return c->ks->taylor(p, static_cast<cudaStream_t>(stream));
 }
 
+int ssb_lts_accumulate(ssb_ctx* c, ssb_array_t buffers, ssb_array_t idofs, int reset, long long n, void* stream) {
+  if (c == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  AccumulateParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.buffers = conv(buffers);
+  p.idofs = conv(idofs);
+  if (!p.buffers.present() || !p.idofs.present()) {
+    return SSB_EINVAL;
+  }
+  p.n = n;
+  p.vec4PerElem = 9 * c->ldq / 4;
+  p.reset = reset;
+  return c->ks->accumulate(p, static_cast<cudaStream_t>(stream));
+}
+
 int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
               ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types, const uint8_t* face_rel,
               long long n, const int* perm, void* stream) {

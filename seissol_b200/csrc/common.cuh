@@ -161,6 +161,14 @@ __device__ __forceinline__ double pk_make(const double (&a)[1]) { return a[0]; }
 __device__ __forceinline__ float2 pk_sel01(float2 a, float2 b) { return make_float2(a.x, b.y); }
 __device__ __forceinline__ double pk_sel01(double a, double) { return a; }
 
+// keep lane v of a packed value only if keep[v], else exactly zero (a select, not a multiply: the dropped lane may
+// hold NaN/Inf computed from stale shared memory)
+__device__ __forceinline__ float2 pk_keep(float2 a, const bool (&keep)[2]) {
+  return make_float2(keep[0] ? a.x : 0.f, keep[1] ? a.y : 0.f);
+}
+__device__ __forceinline__ float pk_keep(float a, const bool (&keep)[1]) { return keep[0] ? a : 0.f; }
+__device__ __forceinline__ double pk_keep(double a, const bool (&keep)[1]) { return keep[0] ? a : 0.0; }
+
 // 4 consecutive packed entries from a lane-interleaved column ([k][V] reals)
 __device__ __forceinline__ void ldv4(float2 (&v)[4], const float* p) {
   const float4 a = *reinterpret_cast<const float4*>(p);

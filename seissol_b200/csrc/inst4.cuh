@@ -130,7 +130,19 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
-const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, NP * VL, NP * VL, localEntry, neighEntry, taylorEntry};
+int accumulateEntry(const AccumulateParams& p, cudaStream_t stream) {
+  if (p.n <= 0) {
+    return 0;
+  }
+  long long blocks = (p.n * p.vec4PerElem + 255) / 256;
+  if (blocks > 148LL * 16) {
+    blocks = 148LL * 16;
+  }
+  k_lts_accumulate<Real><<<unsigned(blocks), 256, 0, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
+const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, NP * VL, NP * VL, localEntry, neighEntry, taylorEntry, accumulateEntry};
 
 }  // namespace
 

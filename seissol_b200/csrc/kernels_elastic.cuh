@@ -643,6 +643,18 @@ __global__ void __launch_bounds__(blockThreads(NP), 2) k_neigh(const NeighParams
         }
       }
     }
+    {
+      // faces without a regular neighbor: no tile was loaded, F was computed from stale shared memory -> exact zero
+      bool keep[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        keep[v] = ft[v][f] == 0;
+      }
+#pragma unroll
+      for (int i = 0; i < B2P; ++i) {
+        F[i] = pk_keep(F[i], keep);
+      }
+    }
     R* const Fe = smem + P::offF + g * P::SEF + (f & 1) * kNQ * B2P * V;
     if (active) {
 #pragma unroll
@@ -709,6 +721,36 @@ __global__ void __launch_bounds__(256) k_taylor(const TaylorParams p) {
     }
     R* dst = static_cast<R*>(const_cast<void*>(p.idofs.at(el))) + c * p.ldg + k0;
     st4(dst, out[0], out[1], out[2], out[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LTS buffer accumulation: buffers[i] = reset ? idofs[i] : buffers[i] + idofs[i] for cells whose neighbors in a
+// larger time cluster read the sum of two sub-steps (LtsSetup::accumulateBuffers; TimeCluster.cpp:508-530,
+// device::algorithms kernel_streamBatchedData / kernel_accumulateBatchedData).
+struct AccumulateParams {
+  ElemArray buffers;
+  ElemArray idofs;
+  long long n;
+  int vec4PerElem;  // tensor size / 4 reals
+  int reset;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_lts_accumulate(const AccumulateParams p) {
+  const long long total = p.n * p.vec4PerElem;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const long long el = i / p.vec4PerElem;
+    const int off = 4 * static_cast<int>(i - el * p.vec4PerElem);
+    R* dst = static_cast<R*>(const_cast<void*>(p.buffers.at(el))) + off;
+    R a[4];
+    ld4(a, static_cast<const R*>(p.idofs.at(el)) + off);
+    if (!p.reset) {
+      R b[4];
+      ld4(b, dst);
+      a[0] += b[0]; a[1] += b[1]; a[2] += b[2]; a[3] += b[3];
+    }
+    st4(dst, a[0], a[1], a[2], a[3]);
   }
 }
 

@@ -491,13 +491,19 @@ __device__ __forceinline__ void neighBody4(const NeighParams& p, unsigned char* 
         a[c] = pk_make(tv);
       }
       {
+        // faces without a regular neighbor: no tile was loaded, G came from stale shared memory -> F exactly zero
+        bool keep[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          keep[v] = ((ftReg[v] >> f) & 1u) != 0;
+        }
         PT F[B2P / 2];
         const SrcPk<R> gcol{Gb + q * B2P * V};
         G::template fP<R, H>(h0, F, gcol);
         if (active) {
 #pragma unroll
           for (int pc = 0; pc < B2P / 4; ++pc) {
-            stv2(Fb + (q * B2P + 4 * pc + 2 * H) * V, F[2 * pc], F[2 * pc + 1]);
+            stv2(Fb + (q * B2P + 4 * pc + 2 * H) * V, pk_keep(F[2 * pc], keep), pk_keep(F[2 * pc + 1], keep));
           }
         }
         if constexpr (V > 1) {
@@ -506,7 +512,7 @@ __device__ __forceinline__ void neighBody4(const NeighParams& p, unsigned char* 
             if (active) {
 #pragma unroll
               for (int pc = 0; pc < B2P / 4; ++pc) {
-                stLane1(Fb + (q * B2P + 4 * pc + 2 * H) * V, F[2 * pc], F[2 * pc + 1]);
+                stLane1(Fb + (q * B2P + 4 * pc + 2 * H) * V, pk_keep(F[2 * pc], keep), pk_keep(F[2 * pc + 1], keep));
               }
             }
           }

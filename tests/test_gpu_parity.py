@@ -114,6 +114,33 @@ def test_neighbor(gpu, order, dt, sort):
     assert rel_l2(data.to_logical(data.dofs) - host["Q"], want - host["Q"]) < 50 * step_tol(dt)
 
 
+@pytest.mark.parametrize("order,dt", [(6, np.float32), (6, np.float64)])
+def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt):
+    """Faces without a regular neighbor load no tile: whatever the previous kernel left in shared memory (here: NaN
+    patterns pushed through torch scan/sort kernels) must not leak into the update (regression: NaN * 0)."""
+    torch, api, proxy = gpu
+    n = 4000
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=21)
+    rng = np.random.default_rng(1)
+    host["I"] = rng.uniform(-1, 1, host["Q"].shape).astype(dt)
+    host["face_types"][rng.uniform(size=(n, 4)) < 0.3] = 5        # many boundary (outflow) faces, every CTA has some
+    host["face_types"][::2, 0] = 5
+    data = proxy.ProxyData.from_host(ctx, host)
+    data.sort_by_face_relation()
+    for _ in range(3):
+        poison = torch.full((1 << 22,), float("nan"), device=data.device, dtype=torch.float32)
+        poison.cumsum(0)
+        torch.sort(poison)
+        torch.sort(torch.full((1 << 22,), -1, device=data.device, dtype=torch.int32))    # 0xffffffff = NaN pattern
+    proxy.ProxyKernels(ctx, data).neigh()
+    torch.cuda.synchronize()
+    got = data.to_logical(data.dofs)
+    assert np.isfinite(got).all()
+    want = O.neighbor(tab, host["Q"], host["I"], host["neighbors"], O.flux_dense(host["Aminus"]),
+                      host["face_rel"], host["face_types"])
+    assert rel_l2(got, want) < step_tol(dt)
+
+
 @pytest.mark.parametrize("order,dt", [(6, np.float32), (6, np.float64), (4, np.float32)])
 def test_all_n_steps(gpu, order, dt):
     """BASELINE.json parity bar: DOFs after N steps of `all` within 1e-5 (f32) / 1e-11 (f64)."""

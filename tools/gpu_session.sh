@@ -26,6 +26,9 @@ visco)
   timeout 900 python -m pytest tests/test_gpu_visco.py -m gpu -x -q > $out/pytest_visco.log 2>&1; echo "exit $?" >> $out/pytest_visco.log
   timeout 300 python tools/quick_bench_visco.py > $out/qb_visco.txt 2>&1
   timeout 300 python tools/quick_bench_visco.py --real 8 --cells 500000 > $out/qb_visco_f64.txt 2>&1 ;;
+lts)
+  timeout 900 python -m pytest tests/test_lts.py -m gpu -x -q > $out/pytest_lts.log 2>&1; echo "exit $?" >> $out/pytest_lts.log
+  timeout 600 python tools/quick_bench_lts.py > $out/qb_lts.txt 2>&1 ;;
 qbf64)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 part)
