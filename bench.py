@@ -236,23 +236,52 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
 
-    # ---- end to end: host buffers in, host buffers out, every step (pinned memory)
-    e2e_steps = max(1, min(steps, 5))
+    # ---- end to end: host buffers in, host buffers out, every step (pinned memory).  The DOFs of a step are
+    #      double-buffered on the device and the three legs run on their own streams, so that the device->host copy of
+    #      step s, the kernels of step s+1 and the host->device copy of step s+2 overlap (PCIe is full duplex); every
+    #      step still moves its complete input and its complete result across PCIe inside the timed region.
+    import copy
+    e2e_steps = max(2, min(steps, 6))
     h_in = torch.empty(data.dofs.shape, dtype=data.dofs.dtype, pin_memory=True)
     h_in.copy_(data.dofs)
-    h_out = torch.empty_like(h_in, pin_memory=True)
-    for _ in range(2):
-        data.dofs.copy_(h_in, non_blocking=True)
-        k.all()
-        h_out.copy_(data.dofs, non_blocking=True)
+    h_out = [torch.empty_like(h_in, pin_memory=True) for _ in range(2)]
+    slots = []
+    for i in range(2):
+        d_i = copy.copy(data)
+        d_i.dofs = data.dofs if i == 0 else torch.empty_like(data.dofs)
+        slots.append((d_i, proxy.ProxyKernels(ctx, d_i)))
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_run(n_steps):
+        for st in range(n_steps):
+            i = st % 2
+            d_i, k_i = slots[i]
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_out[i])          # the previous result of this slot has left the device
+                d_i.dofs.copy_(h_in, non_blocking=True)
+                ev_in[i].record(s_in)
+            stream.wait_event(ev_in[i])
+            k_i.all(stream)
+            ev_done[i].record(stream)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[i])
+                h_out[i].copy_(d_i.dofs, non_blocking=True)
+                ev_out[i].record(s_out)
+        stream.wait_stream(s_out)
+        stream.wait_stream(s_in)
+
+    for ev_ in ev_out:
+        ev_.record(stream)
+    e2e_run(2)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(e2e_steps):
-        data.dofs.copy_(h_in, non_blocking=True)
-        k.all()
-        h_out.copy_(data.dofs, non_blocking=True)
+    s_in.wait_stream(stream)
+    e2e_run(e2e_steps)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -301,7 +330,8 @@ def run_ours(args):
                                   "all_nz_tflops": args.cells / (ms_per_step * 1e-3) * nz * 1e-12}},
             "e2e": {"value": world * args.cells * e2e_steps / (e2e_ms * 1e-3), "unit": "element-updates/s",
                     "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps,
-                    "what": "per step: DOFs pinned host -> device, proxy `all` through the C ABI, DOFs device -> pinned host"},
+                    "what": "per step: DOFs pinned host -> device, proxy `all` through the C ABI, DOFs device -> pinned host; "
+                            "two device slots, copy-in / kernels / copy-out of consecutive steps overlap on three streams"},
             "gpu_launches": 3 * steps,
             "clocks": sampler.result(),
         }
@@ -349,6 +379,8 @@ def run_partitioned(args):
     nxl = max(2, int(round(args.cells / (5.0 * ny * nz))))
     nxl += nxl % 2 if (nxl * world) % 2 else 0
     nx = nxl * world
+    if args.lts > 1:
+        return run_partitioned_lts(args, torch, dist, ctx, nx, ny, nz, rank, world, device, dtype)
     layout, data = D.build_partitioned(torch, dist, nx, ny, nz, rank, world, ctx.B, ctx.ld, dtype, device, scale=2e-3)
     data.sort_by_face_relation()
     coeffs = proxy.integrate_coeffs(ORDER, 0.0, proxy.TIMESTEP)
@@ -456,6 +488,77 @@ def run_partitioned(args):
     return 0
 
 
+def run_partitioned_lts(args, torch, dist, ctx, nx, ny, nz, rank, world, device, dtype):
+    """`--lts C` (N > 1): BASELINE.json configs[4] proper -- the partitioned cube mesh with C rate-2 time clusters (bands in
+    z), per-cluster halo exchange (seissol_b200/lts.py).  One step = one macro step (every cluster reaches t + dt_{C-1});
+    value = element updates of all ranks per second."""
+    from seissol_b200 import lts, partition, proxy
+    from seissol_b200.distributed import element_values_torch
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    layout = partition.build_layout(nx, ny, nz, rank, world, args.lts)
+    plan = lts.build_plan(layout, args.lts)
+    gid = torch.from_numpy(plan.gid).to(device)
+    dofs = torch.zeros((plan.n, 9, ctx.ld), dtype=dtype, device=device)
+    dofs[:, :, :ctx.B] = element_values_torch(torch, gid, 9 * ctx.B, 0, 1.0, dtype).reshape(plan.n, 9, ctx.B)
+    dofs = dofs.reshape(plan.n, 9 * ctx.ld).contiguous()
+    li = element_values_torch(torch, gid, 396, 1, 2e-3, dtype).contiguous()
+    ni = element_values_torch(torch, gid, 324, 2, 2e-3, dtype).contiguous()
+    be = lts.CudaLtsBackend(torch, ctx, plan, dofs, li, ni, dist=dist)
+    solver = lts.LtsSolver(plan, be, ORDER, dt0=proxy.TIMESTEP / 2 ** (args.lts - 1))
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        solver.macro_step()
+    barrier()
+    be.launches = 0
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        solver.macro_step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    red = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([plan.updates_per_macro_step(), plan.n, plan.n_acc, plan.n_der, plan.n_scratch], device=device,
+                       dtype=torch.int64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    finite = bool(torch.isfinite(dofs).all())
+    if rank == 0:
+        ms = float(red.item()) / steps
+        upd, cells, n_acc, n_der, n_tay = (int(v) for v in cnt.tolist())
+        peaks, peak_kind = measured_peaks()
+        all_bytes = proxy.algorithmic_bytes_per_element(ORDER, args.real, KERNEL)
+        achieved = all_bytes * upd / world / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "element-updates/s", "value": upd / (ms * 1e-3), "unit": "element-updates/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.real == 4 else "f64", "data": "synthetic",
+            "gflops_nz": upd / (ms * 1e-3) * proxy.nz_flops_per_element(ORDER, KERNEL) * 1e-9,
+            "config": {"workload": f"cube mesh {nx}x{ny}x{nz} cubes x 5 tetrahedra = {cells} elements, elastic ORDER={ORDER}, "
+                                   f"clustered LTS rate 2 with {args.lts} clusters (bands in z), x-slab partition over {world} GPUs, "
+                                   "per-cluster NCCL halo exchange (BASELINE.json configs[4])",
+                       "cells_per_gpu": cells // world, "updates_per_macro_step": upd,
+                       "gts_updates_for_the_same_simulated_time": cells * 2 ** (args.lts - 1),
+                       "accumulating_cells": n_acc, "cells_with_derivatives": n_der, "taylor_faces": n_tay,
+                       "launches_per_macro_step_per_gpu": be.launches // steps, "finite": finite,
+                       "l2": "inputs exceed L2", "parallelism": f"mesh partition x{world}, LTS"},
+            "roofline": {"bound": "hbm", "kernel": "macro step (all launches)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind, "per": "GPU"},
+            "gpu_launches": be.launches, "clocks": sampler.result(),
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,6 +569,7 @@ def main():
     ap.add_argument("--real", type=int, default=REAL, choices=[4, 8])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange")
+    ap.add_argument("--lts", type=int, default=1, help="N > 1: number of rate-2 time clusters (1 = global time stepping)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent proxy replicas instead of the partitioned mesh")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -141,3 +141,55 @@ def test_lts_cuda_matches_brute_force(built_library, order, dt, bar):
     got = dofs.cpu().numpy().reshape(plan.n, 9, ctx.ld)[:, :, :ctx.B].transpose(0, 2, 1)
     assert rel_l2(got, want) < bar
     assert be.launches > 0
+
+
+def _cuda_lts_rank(rank, world, port, out):
+    """One GPU per rank: partitioned LTS through the C ABI with NCCL; rank-local result saved for the comparison."""
+    from seissol_b200 import api
+    order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    layout = P.build_layout(*dims, rank, world, ncl)
+    plan = L.build_plan(layout, ncl)
+    ctx = api.Context(order, 4)
+    Q = M.element_values(plan.gid, 9 * ctx.B, 0, 1.0, dt).reshape(plan.n, 9, ctx.B)
+    qd = np.zeros((plan.n, 9, ctx.ld), dtype=dt)
+    qd[:, :, :ctx.B] = Q
+    dofs = torch.from_numpy(qd.reshape(plan.n, 9 * ctx.ld)).to(dev)
+    li = torch.from_numpy(M.element_values(plan.gid, 396, 1, 1e-2, dt)).to(dev)
+    ni = torch.from_numpy(M.element_values(plan.gid, 324, 2, 1e-2, dt)).to(dev)
+    be = L.CudaLtsBackend(torch, ctx, plan, dofs, li, ni, dist=dist)
+    solver = L.LtsSolver(plan, be, order, dt0=0.5)
+    for _ in range(2):
+        solver.macro_step()
+    torch.cuda.synchronize()
+    got = dofs.cpu().numpy().reshape(plan.n, 9, ctx.ld)[:, :, :ctx.B].transpose(0, 2, 1)
+    np.save(os.path.join(out, f"cq_{rank}.npy"), got)
+    np.save(os.path.join(out, f"cgid_{rank}.npy"), plan.gid)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_partitioned_lts_cuda_two_gpus(built_library, tmp_path):
+    """2 GPUs, NCCL: the partitioned LTS run through the CUDA kernels matches the brute-force LTS of the whole mesh."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
+    out = str(tmp_path)
+    mp.spawn(_cuda_lts_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+    plan, Q, li, ni = make_problem(order, dt, dims, ncl)
+    tab = O.load_tables(order, dt)
+    star = O.star_dense(li[:, :72].reshape(-1, 3, 24), tab["star_pattern"])
+    want = Q
+    for _ in range(2):
+        want = brute_force_macro_step(tab, order, plan, want, star, O.flux_dense(li[:, 72:].reshape(-1, 4, 81)),
+                                      O.flux_dense(ni.reshape(-1, 4, 81)), dt0=0.5)
+    ref = np.empty_like(want)
+    ref[plan.gid] = want
+    for r in range(2):
+        q, g = np.load(os.path.join(out, f"cq_{r}.npy")), np.load(os.path.join(out, f"cgid_{r}.npy"))
+        assert rel_l2(q, ref[g]) < 1e-5

@@ -29,6 +29,10 @@ visco)
 lts)
   timeout 900 python -m pytest tests/test_lts.py -m gpu -x -q > $out/pytest_lts.log 2>&1; echo "exit $?" >> $out/pytest_lts.log
   timeout 600 python tools/quick_bench_lts.py > $out/qb_lts.txt 2>&1 ;;
+part2lts)
+  timeout 600 python -m pytest tests/test_lts.py -m gpu -x -q > $out/pytest_lts2.log 2>&1; echo "exit $?" >> $out/pytest_lts2.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 5 --warmup 3 --lts 3 > $out/bench_lts2.json 2> $out/bench_lts2.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 --steps 10 --warmup 3 > $out/bench_part2.json 2> $out/bench_part2.err ;;
 qbf64)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 part)
