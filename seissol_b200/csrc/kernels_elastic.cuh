@@ -206,8 +206,11 @@ __device__ __forceinline__ void tmaStoreTensor(R* dst, const R* src, int ldg) {
 }
 
 // ---------------------------------------------------------------------------------------
+#ifndef SSB_MINB_LOCAL
+#define SSB_MINB_LOCAL 2  // resident CTAs per SM the register allocation of k_local is sized for
+#endif
 template <typename R, typename G, int NP, bool ADER, bool LOCAL>
-__global__ void __launch_bounds__(blockThreads(NP), 2) k_local(const LocalParams p) {
+__global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_LOCAL) k_local(const LocalParams p) {
   using P = LocalPlan<R, G, NP>;
   using PT = typename Pk<R>::T;
   constexpr int V = P::V, E = P::E, BP = P::BP, B2P = P::B2P, TEN = P::TEN;
@@ -491,8 +494,11 @@ struct NeighPlan {
   static constexpr size_t bytes = barOffset + 16;
 };
 
+#ifndef SSB_MINB_NEIGH
+#define SSB_MINB_NEIGH 2  // resident CTAs per SM the register allocation of k_neigh is sized for
+#endif
 template <typename R, typename G, int NP>
-__global__ void __launch_bounds__(blockThreads(NP), 2) k_neigh(const NeighParams p) {
+__global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_NEIGH) k_neigh(const NeighParams p) {
   using P = NeighPlan<R, G, NP>;
   using PT = typename Pk<R>::T;
   constexpr int V = P::V, E = P::E, BP = P::BP, B2P = P::B2P, TEN = P::TEN;

@@ -70,11 +70,12 @@ struct ViscoPlan {
   static constexpr int TF = kNQ * B2P;   // face projection
   // predictor: dQ ping-pong | dQane | Iane
   static constexpr int aderReals = padOdd16(2 * TQ + 2 * TA, sizeof(R));
-  // local: I | Iane | two face buffers
-  static constexpr int localReals = padOdd16(TQ + TA + 2 * TF, sizeof(R));
-  // neigh: neighbor tile | two face buffers
-  static constexpr int neighReals = padOdd16(TQ + 2 * TF, sizeof(R));
+  // local: I | Iane | two face buffers | Q | Qane (own DOFs, staged for the final read-modify-write)
+  static constexpr int localReals = padOdd16(2 * TQ + 2 * TA + 2 * TF, sizeof(R));
+  // neigh: neighbor tile | two face buffers | Q | Qane
+  static constexpr int neighReals = padOdd16(2 * TQ + TA + 2 * TF, sizeof(R));
   static constexpr int threads = (kVNE * E + 31) / 32 * 32;
+  // two mbarriers behind the element data
   __host__ __device__ static constexpr size_t bytes(int perElem) { return (size_t(E) * perElem * sizeof(R) + 15) / 16 * 16 + 16; }
 };
 
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_loca
   constexpr int BP = P::BP, B2P = P::B2P, TQ = P::TQ, TA = P::TA, TF = P::TF;
   extern __shared__ __align__(128) unsigned char smemRaw[];
   R* const smem = reinterpret_cast<R*>(smemRaw);
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::bytes(P::localReals) - 16);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::bytes(P::localReals) - 16);  // [0]: I, Iane  [1]: Q, Qane
   const int tid = threadIdx.x;
   const bool active = tid < kVNE * E;
   const int e = active ? tid % E : 0;
@@ -286,8 +287,11 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_loca
   R* const SIq = smem + e * P::localReals;  // I
   R* const SI = SIq + TQ;                    // Iane
   R* const SF = SI + TA;                     // two face buffers
+  R* const SQ = SF + 2 * TF;                 // own Q: arrives while volume and fluxes are computed
+  R* const SA = SQ + TQ;                     // own Qane
   if (tid == 0) {
     mbar_init(bar, E);
+    mbar_init(bar + 1, E);
     mbar_fence_init();
   }
   __syncthreads();
@@ -298,8 +302,12 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_loca
       mbar_arrive_expect_tx(bar, (TQ + TA) * sizeof(R));
       tmaLoadCols<R>(SIq, static_cast<const R*>(p.idofs.at(el)), kNQ, BP, p.ldg, bar);
       tmaLoadCols<R>(SI, static_cast<const R*>(p.idofsAne.at(el)), kVNA, BP, p.ldg, bar);
+      mbar_arrive_expect_tx(bar + 1, (TQ + TA) * sizeof(R));
+      tmaLoadCols<R>(SQ, static_cast<const R*>(p.dofs.at(el)), kNQ, BP, p.ldg, bar + 1);
+      tmaLoadCols<R>(SA, static_cast<const R*>(p.dofsAne.at(el)), kVNA, BP, p.ldg, bar + 1);
     } else {
       mbar_arrive_expect_tx(bar, 0);
+      mbar_arrive_expect_tx(bar + 1, 0);
     }
   }
   const R* li = valid ? static_cast<const R*>(p.localInt.at(el)) : nullptr;
@@ -343,53 +351,58 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_loca
     __syncthreads();
     G::template rDivM<R>(f, ext, JChunks<R, B2P>{Fe, a});
   }
-  if (!valid) {
-    return;  // no barriers below
-  }
-  // kernel::local (viscoelastic2.py:259-277), read-modify-write of the own columns in global memory
-  if (roleA) {
-    R Eq[kVNA];
+  // kernel::local (viscoelastic2.py:259-277) on the staged own DOFs: every thread updates its own columns
+  mbar_wait(bar + 1, 0);
+  if (valid) {
+    if (roleA) {
+      R Eq[kVNA];
 #pragma unroll
-    for (int c = 0; c < kVNA; ++c) {
-      Eq[c] = li[kVOffE + kVNA * q + c];
-    }
+      for (int c = 0; c < kVNA; ++c) {
+        Eq[c] = li[kVOffE + kVNA * q + c];
+      }
 #pragma unroll
-    for (int c = 0; c < kVNA; ++c) {
+      for (int c = 0; c < kVNA; ++c) {
+#pragma unroll
+        for (int k4 = 0; k4 < BP / 4; ++k4) {
+          R t[4];
+          ld4(t, SI + c * BP + 4 * k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ext[4 * k4 + i] = fma(Eq[c], t[i], ext[4 * k4 + i]);
+          }
+        }
+      }
 #pragma unroll
       for (int k4 = 0; k4 < BP / 4; ++k4) {
         R t[4];
-        ld4(t, SI + c * BP + 4 * k4);
+        ld4(t, SQ + q * BP + 4 * k4);
+        st4(SQ + q * BP + 4 * k4, t[0] + ext[4 * k4], t[1] + ext[4 * k4 + 1], t[2] + ext[4 * k4 + 2], t[3] + ext[4 * k4 + 3]);
+      }
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ext[4 * k4 + i] = fma(Eq[c], t[i], ext[4 * k4 + i]);
+      for (int m = 0; m < kVM; ++m) {
+        const int col = pa + 6 * m;
+        const R wm = li[kVOffw + m], Wm = li[kVOffW + m];
+#pragma unroll
+        for (int k4 = 0; k4 < BP / 4; ++k4) {
+          R t[4], u[4];
+          ld4(t, SA + col * BP + 4 * k4);
+          ld4(u, SI + col * BP + 4 * k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            t[i] = fma(Wm, u[i], fma(wm, ext[4 * k4 + i], t[i]));
+          }
+          st4(SA + col * BP + 4 * k4, t[0], t[1], t[2], t[3]);
         }
       }
     }
-    R* qg = static_cast<R*>(const_cast<void*>(p.dofs.at(el))) + q * p.ldg;
-#pragma unroll
-    for (int k4 = 0; k4 < BP / 4; ++k4) {
-      R t[4];
-      ld4(t, qg + 4 * k4);
-      st4(qg + 4 * k4, t[0] + ext[4 * k4], t[1] + ext[4 * k4 + 1], t[2] + ext[4 * k4 + 2], t[3] + ext[4 * k4 + 3]);
-    }
-  } else {
-    R* ag = static_cast<R*>(const_cast<void*>(p.dofsAne.at(el)));
-#pragma unroll
-    for (int m = 0; m < kVM; ++m) {
-      const int col = pa + 6 * m;
-      const R wm = li[kVOffw + m], Wm = li[kVOffW + m];
-#pragma unroll
-      for (int k4 = 0; k4 < BP / 4; ++k4) {
-        R t[4], u[4];
-        ld4(t, ag + col * p.ldg + 4 * k4);
-        ld4(u, SI + col * BP + 4 * k4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          t[i] = fma(Wm, u[i], fma(wm, ext[4 * k4 + i], t[i]));
-        }
-        st4(ag + col * p.ldg + 4 * k4, t[0], t[1], t[2], t[3]);
-      }
-    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (tid < E && el < p.n) {
+    tmaStoreCols<R>(static_cast<R*>(const_cast<void*>(p.dofs.at(el))), SQ, kNQ, BP, p.ldg);
+    tmaStoreCols<R>(static_cast<R*>(const_cast<void*>(p.dofsAne.at(el))), SA, kVNA, BP, p.ldg);
+    tma_store_wait_read();
   }
 }
 
@@ -407,8 +420,11 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_neig
   const int q = active ? tid / E : 0;
   R* const tile = smem + e * P::neighReals;
   R* const SF = tile + TQ;
+  R* const SQ = SF + 2 * TF;   // own Q and Qane: arrive while the four faces are computed (bar[1])
+  R* const SA = SQ + TQ;
   if (tid == 0) {
     mbar_init(bar, E);
+    mbar_init(bar + 1, E);
     mbar_fence_init();
   }
   __syncthreads();
@@ -435,6 +451,13 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_neig
   };
   if (tid < E) {
     loadTile(0);
+    if (el >= 0) {
+      mbar_arrive_expect_tx(bar + 1, (TQ + P::TA) * sizeof(R));
+      tmaLoadCols<R>(SQ, static_cast<const R*>(p.dofs.at(el)), kNQ, BP, p.ldg, bar + 1);
+      tmaLoadCols<R>(SA, static_cast<const R*>(p.dofsAne.at(el)), kVNA, BP, p.ldg, bar + 1);
+    } else {
+      mbar_arrive_expect_tx(bar + 1, 0);
+    }
   }
   const bool roleA = q < kNQ;
   const int pa = roleA ? 0 : q - kNQ;
@@ -480,35 +503,40 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_neig
     }
     G::template rDivM<R>(f, ext, JChunks<R, B2P>{Fe, a});
   }
-  if (!valid) {
-    return;
-  }
-  // kernel::neighbor (viscoelastic2.py:317-334)
-  if (roleA) {
-    R* qg = static_cast<R*>(const_cast<void*>(p.dofs.at(el))) + q * p.ldg;
-#pragma unroll
-    for (int k4 = 0; k4 < BP / 4; ++k4) {
-      R t[4];
-      ld4(t, qg + 4 * k4);
-      st4(qg + 4 * k4, t[0] + ext[4 * k4], t[1] + ext[4 * k4 + 1], t[2] + ext[4 * k4 + 2], t[3] + ext[4 * k4 + 3]);
-    }
-  } else {
-    R* ag = static_cast<R*>(const_cast<void*>(p.dofsAne.at(el)));
-#pragma unroll
-    for (int m = 0; m < kVM; ++m) {
-      const int col = pa + 6 * m;
-      const R wm = ni[4 * kVA + m];
+  // kernel::neighbor (viscoelastic2.py:317-334) on the staged own DOFs
+  mbar_wait(bar + 1, 0);
+  if (valid) {
+    if (roleA) {
 #pragma unroll
       for (int k4 = 0; k4 < BP / 4; ++k4) {
         R t[4];
-        ld4(t, ag + col * p.ldg + 4 * k4);
+        ld4(t, SQ + q * BP + 4 * k4);
+        st4(SQ + q * BP + 4 * k4, t[0] + ext[4 * k4], t[1] + ext[4 * k4 + 1], t[2] + ext[4 * k4 + 2], t[3] + ext[4 * k4 + 3]);
+      }
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          t[i] = fma(wm, ext[4 * k4 + i], t[i]);
+      for (int m = 0; m < kVM; ++m) {
+        const int col = pa + 6 * m;
+        const R wm = ni[4 * kVA + m];
+#pragma unroll
+        for (int k4 = 0; k4 < BP / 4; ++k4) {
+          R t[4];
+          ld4(t, SA + col * BP + 4 * k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            t[i] = fma(wm, ext[4 * k4 + i], t[i]);
+          }
+          st4(SA + col * BP + 4 * k4, t[0], t[1], t[2], t[3]);
         }
-        st4(ag + col * p.ldg + 4 * k4, t[0], t[1], t[2], t[3]);
       }
     }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (tid < E && el >= 0) {
+    tmaStoreCols<R>(static_cast<R*>(const_cast<void*>(p.dofs.at(el))), SQ, kNQ, BP, p.ldg);
+    tmaStoreCols<R>(static_cast<R*>(const_cast<void*>(p.dofsAne.at(el))), SA, kVNA, BP, p.ldg);
+    tma_store_wait_read();
   }
 }
 

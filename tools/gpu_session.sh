@@ -33,6 +33,19 @@ part2lts)
   timeout 600 python -m pytest tests/test_lts.py -m gpu -x -q > $out/pytest_lts2.log 2>&1; echo "exit $?" >> $out/pytest_lts2.log
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 5 --warmup 3 --lts 3 > $out/bench_lts2.json 2> $out/bench_lts2.err
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 --steps 10 --warmup 3 > $out/bench_part2.json 2> $out/bench_part2.err ;;
+ab4)
+  for v in c4 c3; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py > $out/qb_$v.txt 2>&1
+  done
+  timeout 300 python tools/quick_bench.py > $out/qb_base.txt 2>&1 ;;
+ncu3)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_visco' --launch-skip 6 -c 3 -f -o $out/full_visco \
+      python tools/quick_bench_visco.py --cells 200000 --steps 1 --kernels all > $out/ncu_visco.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 6 -c 3 -f -o $out/full_f64 \
+      python tools/quick_bench.py --real 8 --cells 148000 --steps 1 --kernels all > $out/ncu_f64.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp|k_friction|k_neigh_dr' --launch-skip 5 -c 4 -f -o $out/full_dr \
+      python tools/quick_bench_dr.py --steps 1 > $out/ncu_dr.log 2>&1 ;;
 qbf64)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 part)
