@@ -106,3 +106,37 @@ def test_visco_context_rejects_unsupported():
         api.Context(6, 4, equation=1, mechanisms=3)
     with pytest.raises(api.SsbError):
         api.Context(5, 4, equation=1, mechanisms=2)
+
+
+def test_visco_empty_batch_and_reference_layout(gpu):
+    """n = 0 is a no-op for every entry point; the reference's 64-byte padded layout (ld = 48 in single precision at
+    order 5, yateto/arch.py:197-198) gives the same numbers as the compact one."""
+    torch, api, proxy = gpu
+    dt = np.float32
+    tab = O.load_tables(5, dt)
+    d = V.proxy_data(5, 40, dt, seed=4)
+    coeffs = O.time_integrate_coeffs(5, 0.0, 1.0, dt)
+    ctx = api.Context(5, 4, equation=1, mechanisms=3)
+    data = proxy.ViscoProxyData.from_host(ctx, d)
+    before = data.dofs.clone()
+    ctx.visco_ader(api.strided(data.dofs), api.strided(data.dofs_ane), api.strided(data.buffers), api.strided(data.buffers_ane),
+                   api.strided(data.local_int), coeffs, 0)
+    ctx.visco_local(api.strided(data.dofs), api.strided(data.dofs_ane), api.strided(data.buffers), api.strided(data.buffers_ane),
+                    api.strided(data.local_int), data.face_types, 0)
+    ctx.visco_neigh(api.strided(data.dofs), api.strided(data.dofs_ane), api.strided(data.buffers), api.strided(data.neigh_int),
+                    data.face_types, data.face_rel, 0, nb_idx=data.neighbors)
+    torch.cuda.synchronize()
+    assert torch.equal(before, data.dofs)
+    ref = api.Context(5, 4, equation=1, mechanisms=3, reference_layout=True)
+    assert ref.ld == 48 and ctx.ld == 36
+    data_r = proxy.ViscoProxyData.from_host(ref, d)
+    for dd, cc in ((data, ctx), (data_r, ref)):
+        k = proxy.ViscoProxyKernels(cc, dd)
+        k.all()
+    torch.cuda.synchronize()
+    star, E = V.star_dense(d["star"]), V.e_dense(d["E"], 3)
+    want = V.proxy_step(tab, dict(d), coeffs, "all")
+    for dd in (data, data_r):
+        assert rel_l2(dd.q_to_logical(dd.dofs), want["Q"]) < tol(dt)
+        assert rel_l2(dd.ane_to_logical(dd.dofs_ane), want["Qane"]) < tol(dt)
+    del star, E
