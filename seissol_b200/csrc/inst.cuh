@@ -29,6 +29,17 @@ inline unsigned gridFor(long long batches) {
   return static_cast<unsigned>(batches);
 }
 
+// development aid: SSB_SMEM_PAD=<bytes> requests extra dynamic shared memory per CTA, i.e. lowers the number of
+// resident CTAs per SM without recompiling (occupancy experiments)
+inline size_t smemPad() {
+  static long pad = -1;
+  if (pad < 0) {
+    const char* e = std::getenv("SSB_SMEM_PAD");
+    pad = e != nullptr ? std::atol(e) : 0;
+  }
+  return static_cast<size_t>(pad);
+}
+
 // Traits binding the generated operator code of one order to the kernel templates.
 struct Gen {
   static constexpr int kOrder = SSB_GEN::kOrder;
@@ -75,7 +86,7 @@ int launchLocal(const LocalParams& p, cudaStream_t stream) {
   auto kern = k_local<Real, Gen, EL, ADER, LOCAL>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes));
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
     if (err != cudaSuccess) {
       return int(err);
     }
@@ -85,7 +96,7 @@ int launchLocal(const LocalParams& p, cudaStream_t stream) {
     return 0;
   }
   const unsigned grid = gridFor((p.n + EL * VL - 1) / (EL * VL));
-  kern<<<grid, blockThreads(EL), P::bytes, stream>>>(p);
+  kern<<<grid, blockThreads(EL), P::bytes + smemPad(), stream>>>(p);
   return int(cudaGetLastError());
 }
 
@@ -104,7 +115,7 @@ int neighEntry(const NeighParams& p, cudaStream_t stream) {
   auto kern = k_neigh<Real, Gen, EN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes));
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
     if (err != cudaSuccess) {
       return int(err);
     }
@@ -114,7 +125,7 @@ int neighEntry(const NeighParams& p, cudaStream_t stream) {
     return 0;
   }
   const unsigned grid = gridFor((p.n + EN * VL - 1) / (EN * VL));
-  kern<<<grid, blockThreads(EN), P::bytes, stream>>>(p);
+  kern<<<grid, blockThreads(EN), P::bytes + smemPad(), stream>>>(p);
   return int(cudaGetLastError());
 }
 

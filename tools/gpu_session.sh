@@ -46,6 +46,10 @@ ncu3)
       python tools/quick_bench.py --real 8 --cells 148000 --steps 1 --kernels all > $out/ncu_f64.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp|k_friction|k_neigh_dr' --launch-skip 5 -c 4 -f -o $out/full_dr \
       python tools/quick_bench_dr.py --steps 1 > $out/ncu_dr.log 2>&1 ;;
+occ)
+  timeout 300 python tools/quick_bench.py > $out/qb_occ2.txt 2>&1
+  SSB_SMEM_PAD=20000 timeout 300 python tools/quick_bench.py > $out/qb_occ1.txt 2>&1
+  SSB_SMEM_PAD=20000 SSB_PERSISTENT=1 timeout 300 python tools/quick_bench.py > $out/qb_occ1_persist.txt 2>&1 ;;
 qbf64)
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 part)
