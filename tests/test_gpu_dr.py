@@ -178,3 +178,91 @@ def test_neigh_dr_nodal_flux(gpu, order, dt):
     got = data.to_logical(data.dofs)
     assert rel_l2(got, want) < tol(dt)
     assert rel_l2(got - host["Q"], want - host["Q"]) < 50 * tol(dt)
+
+
+@pytest.mark.parametrize("order", [4, 6])
+def test_fault_time_step_chain(gpu, order):
+    """One time step across a fault, all kernels chained on the device exactly as TimeCluster does
+    (ader with derivatives -> local (DR faces skipped) -> godunov_dr interpolation of both sides -> LSW friction ->
+    neighbor flux of the regular faces + nodal flux of the imposed state), against the same chain of oracle functions.
+    Checks that the layouts the kernels hand to each other agree (QInterpolated, ImposedState, CellDRMapping pointers)."""
+    torch, api, proxy = gpu
+    dt, step = np.float64, 1e-3
+    ctx = api.Context(order, 8)
+    tab = O.load_tables(order, dt)
+    rng = np.random.default_rng(17)
+    n, m = 60, 11
+    P = (order + 1) ** 2
+    host = O.proxy_data(order, n, dt, seed=23)
+    # fault faces: distinct (cell, side) pairs for the plus and the minus side
+    slots = rng.permutation(4 * n)[:2 * m]
+    plus_cell, plus_side = slots[:m] // 4, slots[:m] % 4
+    minus_cell, minus_side = slots[m:] // 4, slots[m:] % 4
+    rel = rng.integers(1, 4, m)           # DRFaceInformation::faceRelation of the minus side (orientation + 1)
+    ft = np.zeros((n, 4), dtype=np.uint8)
+    ft[plus_cell, plus_side] = 3
+    ft[minus_cell, minus_side] = 3
+    host["face_types"] = ft
+    info = np.stack([plus_side, minus_side, rel], 1).astype(np.uint8)
+    tinv = rng.uniform(-1, 1, (m, 9, 9)).astype(dt)
+    flux_solver = (rng.uniform(-1, 1, (2 * m, 9, 9)) * 1e-9).astype(dt)     # rows: plus faces, then minus faces
+    st, imp, params = F.fault_state("lsw", m, order, dt)
+    c_int = O.time_integrate_coeffs(order, 0.0, step, dt)
+    pts, _ = proxy.gauss_legendre_points(order, step)
+    c_pts = np.stack([proxy.point_coeffs(order, tau) for tau in pts]).astype(dt)
+    fp, dts, wts = proxy.friction_params(order, step, full_update_time=0.0, healing_threshold=params.healingThreshold, t0=params.t0)
+
+    # ---- oracle chain
+    star = O.star_dense(host["star"], tab["star_pattern"])
+    I, ders = O.ader(tab, host["Q"], star, c_int, True)
+    q_loc = O.local(tab, host["Q"], I, star, O.flux_dense(host["Aplus"]), ft)
+    qip, qim = O.dr_interpolate(tab, [d[plus_cell] for d in ders], [d[minus_cell] for d in ders], tinv, info, c_pts)
+    st_o = {k: v.copy() for k, v in st.items()}
+    law = F.LinearSlipWeakening(params, tab["resample"])
+    imp_plus, imp_minus = F.evaluate(law, st_o, imp, qip, qim, 0.0, dts, wts)
+    dr_index = np.zeros((n, 4), dtype=np.int64)
+    dr_side = np.zeros((n, 4), dtype=np.uint8)
+    dr_rel = np.zeros((n, 4), dtype=np.uint8)
+    dr_index[plus_cell, plus_side] = np.arange(m)
+    dr_side[plus_cell, plus_side] = plus_side
+    dr_index[minus_cell, minus_side] = m + np.arange(m)
+    dr_side[minus_cell, minus_side] = minus_side
+    dr_rel[minus_cell, minus_side] = rel
+    want = O.neighbor(tab, q_loc, I, host["neighbors"], O.flux_dense(host["Aminus"]), host["face_rel"], ft,
+                      dr={"godunov": np.concatenate([imp_plus, imp_minus]), "fluxSolver": flux_solver, "index": dr_index,
+                          "side": dr_side, "rel": dr_rel})
+
+    # ---- device chain
+    dev = torch.device("cuda")
+    data = proxy.ProxyData.from_host(ctx, host)
+    derivs = torch.zeros((n, ctx.dersize), device=dev, dtype=torch.float64)
+    ctx.ader(api.strided(data.dofs), api.strided(data.buffers), api.strided(derivs), api.strided(data.local_int), c_int, n)
+    ctx.local(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.local_int), data.face_types, n)
+    stride = derivs.stride(0) * derivs.element_size()
+    pp = (derivs.data_ptr() + torch.from_numpy(plus_cell).to(dev) * stride).contiguous()
+    pm = (derivs.data_ptr() + torch.from_numpy(minus_cell).to(dev) * stride).contiguous()
+    qp = torch.zeros((m, order, 9, ctx.ppad), device=dev, dtype=torch.float64)
+    qm = torch.zeros_like(qp)
+    tinv_mem = torch.from_numpy(np.ascontiguousarray(tinv.transpose(0, 2, 1)).reshape(m, 81)).to(dev)
+    ctx.dr_interp(api.pointer_table(pp), api.pointer_table(pm), tinv_mem, torch.from_numpy(info).to(dev), qp, qm, c_pts, m)
+    d, names = _friction_device_data(torch, ctx, proxy, st, imp, np.zeros((m, order, P, 9), dtype=dt),
+                                     np.zeros((m, order, P, 9), dtype=dt), tab["resample"], "lsw")
+    d["q_plus"], d["q_minus"] = qp, qm
+    ctx.friction("lsw", d, fp, m)
+    imposed = torch.cat([d["imposed_plus"], d["imposed_minus"]]).contiguous()                 # [2m, 9, ppad]
+    fs_mem = torch.from_numpy(np.ascontiguousarray(flux_solver.transpose(0, 2, 1)).reshape(2 * m, 81)).to(dev)
+    idx = torch.from_numpy(dr_index).to(dev)
+    gp = (imposed.data_ptr() + idx * (9 * ctx.ppad * 8)).contiguous()
+    fsp = (fs_mem.data_ptr() + idx * (81 * 8)).contiguous()
+    sr = torch.from_numpy(np.stack([dr_side, dr_rel], -1).astype(np.uint8)).to(dev).contiguous()
+    ctx.neigh(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.neigh_int), data.face_types, data.face_rel, n,
+              nb_idx=data.neighbors)
+    ctx.neigh_dr(api.strided(data.dofs), gp, fsp, sr, data.face_types, n)
+    torch.cuda.synchronize()
+    assert rel_l2(proxy.points_from_device(ctx, qp.cpu().numpy(), P), qip) < 5e-15
+    assert rel_l2(proxy.points_from_device(ctx, d["imposed_plus"].cpu().numpy(), P), imp_plus) < 1e-11
+    assert rel_l2(proxy.points_from_device(ctx, d["imposed_minus"].cpu().numpy(), P), imp_minus) < 1e-11
+    got = data.to_logical(data.dofs)
+    assert rel_l2(got, want) < 1e-11
+    assert rel_l2(got - q_loc, want - q_loc) < 1e-9            # the neighbor + nodal-flux update itself
+    assert np.abs(d["slip_rate_magnitude"].cpu().numpy()[:, :P] - st_o["slipRateMagnitude"]).max() < 1e-9
