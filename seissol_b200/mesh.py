@@ -45,10 +45,13 @@ class CubeMesh:
     Periodic in x (ranks form a ring); y and z end at the domain boundary.  Element ids are global:
     gid = 5 * ((ix * ny + iy) * nz + iz) + t, so that every rank derives the same data for the same element."""
 
-    def __init__(self, nx, ny, nz, x0=0, x1=None):
+    def __init__(self, nx, ny, nz, x0=0, x1=None, periodic_yz=False):
         if nx % 2:
             raise ValueError("nx must be even (parity split + periodicity in x)")
+        if periodic_yz and (ny % 2 or nz % 2 or min(nx, ny, nz) < 4):
+            raise ValueError("a fully periodic mesh needs even ny, nz and at least 4 cubes per direction")
         self.nx, self.ny, self.nz = nx, ny, nz
+        self.periodic_yz = periodic_yz
         x1 = nx if x1 is None else x1
         self.x0, self.x1 = x0, x1
         ix = np.arange(x0, x1)
@@ -56,14 +59,19 @@ class CubeMesh:
         gx, gy, gz = gx.ravel(), gy.ravel(), gz.ravel()
         parity = (gx + gy + gz) % 2
         corners = np.where(parity[:, None, None] == 0, _EVEN[None], _ODD[None])        # [cubes, 5, 4]
-        cx = (gx[:, None, None] + (corners & 1)) % nx
-        cy = gy[:, None, None] + ((corners >> 1) & 1)
-        cz = gz[:, None, None] + ((corners >> 2) & 1)
-        vertices = ((cx * (ny + 1) + cy) * (nz + 1) + cz).reshape(-1, 4).astype(np.int64)
+        ux = gx[:, None, None] + (corners & 1)
+        uy = gy[:, None, None] + ((corners >> 1) & 1)
+        uz = gz[:, None, None] + ((corners >> 2) & 1)
+        cx = ux % nx
+        py, pz = (ny, nz) if periodic_yz else (ny + 1, nz + 1)
+        cy, cz = uy % py, uz % pz
+        vertices = ((cx * py + cy) * pz + cz).reshape(-1, 4).astype(np.int64)
+        coords = np.stack([ux, uy, uz], -1).reshape(-1, 4, 3).astype(np.float64)      # unwrapped vertex coordinates
         cube = (gx * ny + gy) * nz + gz
         self.gid = (5 * cube[:, None] + np.arange(5)[None]).reshape(-1).astype(np.int64)
         perm = _A4[(self.gid * 2654435761 >> 7) % 12]
         self.vertices = np.take_along_axis(vertices, perm, axis=1)
+        self.coords = np.take_along_axis(coords, perm[:, :, None], axis=1)   # [n, 4, 3] in the element's local numbering
         self.cube_x = np.repeat(gx, 5)
         self.cube_z = np.repeat(gz, 5)
         self.n = self.vertices.shape[0]

@@ -1,0 +1,114 @@
+"""Physics check of the whole scheme: elastic plane waves in a fully periodic cube mesh converge to the exact solution
+at the order of the discretisation.  Uses the restated cell-local matrix set-up (seissol_b200/material.py, SURVEY.md §8f
+item 1: star matrices, Godunov flux solvers from geometry + material), the modal basis (seissol_b200/basis.py) and
+  * CPU: the numpy oracle as the time stepper,
+  * GPU (-m gpu): the CUDA kernels through the C ABI, which must reproduce the oracle run and its error level."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import aderdg as O
+from seissol_b200 import basis as Bs
+from seissol_b200 import material as Mt
+from seissol_b200 import mesh as M
+
+LAM, MU, RHO = 2.0, 1.0, 1.0
+
+
+def setup(order, n, kind, dtype=np.float64):
+    tab = O.load_tables(order, dtype)
+    m = M.CubeMesh(n, n, n, periodic_yz=True)
+    h = 1.0 / n
+    coords = m.coords * h
+    N = m.n
+    star, ap, am = Mt.cell_local_matrices(coords, m.neighbors, np.full(N, LAM), np.full(N, MU), np.full(N, RHO),
+                                          tab["star_pattern"])
+    f, _ = Mt.plane_wave(LAM, MU, RHO, (1, 1, 1), 1, 1.0, kind)
+    Q = Bs.project(order, coords, lambda x: f(x, 0.0))
+    cp = np.sqrt((LAM + 2 * MU) / RHO)
+    d = {"Q": Q.astype(dtype), "star": star.astype(dtype), "Aplus": ap.astype(dtype), "Aminus": am.astype(dtype),
+         "face_rel": m.face_rel, "neighbors": m.neighbors, "face_types": np.zeros((N, 4), dtype=np.uint8)}
+    return tab, coords, f, d, 0.25 * h / (cp * (2 * order - 1))
+
+
+def run_oracle(order, n, kind, t_end=0.05):
+    tab, coords, f, d, dt = setup(order, n, kind)
+    steps = int(np.ceil(t_end / dt))
+    coeffs = O.time_integrate_coeffs(order, 0.0, t_end / steps)
+    for _ in range(steps):
+        d = O.proxy_step(tab, d, coeffs, "all")
+    err = np.linalg.norm(Bs.l2_error(order, coords, d["Q"], lambda x: f(x, t_end)))
+    ref = np.linalg.norm(Bs.l2_error(order, coords, 0 * d["Q"], lambda x: f(x, t_end)))
+    proj = np.linalg.norm(Bs.l2_error(order, coords, Bs.project(order, coords, lambda x: f(x, t_end)), lambda x: f(x, t_end)))
+    return err / ref, proj / ref, d["Q"], steps
+
+
+def test_basis_matches_operator_tables():
+    """The Dubiner basis restated here is the one the operator tables were generated for:
+    kDivM = M^-1 K, kDivMT = M^-1 K^T with K[k, l] = int dphi_k/dxi phi_l (mass matrix diagonal)."""
+    order = 4
+    tab = O.load_tables(order, np.float64)
+    pts, w = Bs.tet_quadrature(order + 2)
+    phi = Bs.dubiner(order, pts[:, 0], pts[:, 1], pts[:, 2])
+    mass = np.einsum("m,mk,ml->kl", w, phi, phi)
+    assert abs(w.sum() - 1.0 / 6.0) < 1e-14 and np.abs(mass - np.diag(np.diag(mass))).max() < 1e-14
+    h = 1e-6
+    for d in range(3):
+        sh = [h * (d == i) for i in range(3)]
+        dphi = (Bs.dubiner(order, pts[:, 0] + sh[0], pts[:, 1] + sh[1], pts[:, 2] + sh[2])
+                - Bs.dubiner(order, pts[:, 0] - sh[0], pts[:, 1] - sh[1], pts[:, 2] - sh[2])) / (2 * h)
+        K = np.einsum("m,mk,ml->kl", w, dphi, phi)
+        assert np.abs(np.diag(1 / np.diag(mass)) @ K - tab["kDivM"][d]).max() < 1e-7
+        assert np.abs(np.diag(1 / np.diag(mass)) @ K.T + tab["kDivMT"][d]).max() < 1e-7     # load_tables negates kDivMT
+
+
+def test_flux_solver_properties():
+    """Godunov state: QgodLocal + QgodNeighbor = I; rotation: T Tinv = I; homogeneous material: AplusT + AminusT is the
+    rotated normal flux matrix scaled by the face, independent of the tangent choice."""
+    ql, qn = Mt.godunov_state_T(LAM, MU, RHO, 1.3 * LAM, 0.7 * MU, 1.1 * RHO)
+    assert np.abs(ql + qn - np.eye(9)).max() < 1e-14
+    n = np.array([1.0, 2.0, 2.0]) / 3
+    s = np.array([2.0, 1.0, -2.0]) / 3
+    T, Ti = Mt.rotation_matrices(n, s, np.cross(n, s))
+    assert np.abs(T @ Ti - np.eye(9)).max() < 1e-14
+    # sum of both flux solvers = normal flux: sum_d n_d A_d^T (consistency of the numerical flux)
+    at = Mt.coefficient_matrix_T(LAM, MU, RHO, 0)
+    ql, qn = Mt.godunov_state_T(LAM, MU, RHO, LAM, MU, RHO)
+    total = Ti.T @ ((ql + qn) @ at) @ T.T
+    want = sum(n[d] * Mt.coefficient_matrix_T(LAM, MU, RHO, d) for d in range(3))
+    assert np.abs(total - want).max() < 1e-13
+
+
+@pytest.mark.parametrize("order,kind", [(3, "P"), (3, "S"), (4, "P")])
+def test_plane_wave_convergence(order, kind):
+    e4, p4, _, _ = run_oracle(order, 4, kind)
+    e8, p8, _, _ = run_oracle(order, 8, kind)
+    rate = np.log2(e4 / e8)
+    assert rate > order - 0.5, (e4, e8, rate)
+    assert e8 < 2.0 * p8            # the discretisation error stays at the level of the projection error
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order,dt,bar", [(4, np.float64, 1e-11), (4, np.float32, 1e-5), (6, np.float32, 1e-5)])
+def test_plane_wave_cuda(built_library, order, dt, bar):
+    import torch
+    from seissol_b200 import api, proxy
+    n, kind, t_end = 4, "P", 0.05
+    tab, coords, f, d, step = setup(order, n, kind, dt)
+    steps = int(np.ceil(t_end / step))
+    coeffs = O.time_integrate_coeffs(order, 0.0, t_end / steps, dt)
+    ctx = api.Context(order, np.dtype(dt).itemsize)
+    data = proxy.ProxyData.from_host(ctx, d)
+    data.sort_by_face_relation()
+    k = proxy.ProxyKernels(ctx, data)
+    k.coeffs = coeffs
+    want = dict(d)
+    for _ in range(steps):
+        k.all()
+        want = O.proxy_step(tab, want, coeffs, "all")
+    torch.cuda.synchronize()
+    got = data.to_logical(data.dofs)
+    assert rel_l2(got, want["Q"]) < bar
+    err = np.linalg.norm(Bs.l2_error(order, coords, got.astype(np.float64), lambda x: f(x, t_end)))
+    ref = np.linalg.norm(Bs.l2_error(order, coords, 0 * got.astype(np.float64), lambda x: f(x, t_end)))
+    assert err / ref < (2e-2 if order == 4 else 2e-3)
