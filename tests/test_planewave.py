@@ -112,3 +112,50 @@ def test_plane_wave_cuda(built_library, order, dt, bar):
     err = np.linalg.norm(Bs.l2_error(order, coords, got.astype(np.float64), lambda x: f(x, t_end)))
     ref = np.linalg.norm(Bs.l2_error(order, coords, 0 * got.astype(np.float64), lambda x: f(x, t_end)))
     assert err / ref < (2e-2 if order == 4 else 2e-3)
+
+
+def test_plane_wave_lts():
+    """Clustered LTS (3 clusters, rate 2) on the periodic mesh propagates the plane wave as accurately as global time
+    stepping with the smallest step: physics-level check of the LTS schedule and its buffer/derivative plumbing."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from lts_support import NumpyLtsBackend
+    from seissol_b200 import lts as L
+    from seissol_b200.partition import RankLayout
+    order, n, t_end = 4, 8, 0.05
+    tab = O.load_tables(order, np.float64)
+    m = M.CubeMesh(n, n, n, periodic_yz=True)
+    coords = m.coords / n
+    N = m.n
+    band = np.array([0, 0, 1, 1, 2, 2, 1, 1])                 # clusters as bands in z, periodic, neighbors differ by <= 1
+    cluster = band[m.cube_z]
+    layout = RankLayout(rank=0, world=1, n_own=N, n_ghost=0, n_copy=0, gid=np.arange(N), cluster=cluster,
+                        neighbors=m.neighbors, face_rel=m.face_rel, face_types=np.zeros((N, 4), dtype=np.uint8))
+    plan = L.build_plan(layout, 3)
+    assert all(r.end > r.start for r in plan.ranges) and plan.n_acc > 0
+    pc = coords[plan.gid]                                      # geometry in the plan's cell order
+    star, ap, am = Mt.cell_local_matrices(pc, plan.neighbors, np.full(N, LAM), np.full(N, MU), np.full(N, RHO),
+                                          tab["star_pattern"])
+    f, _ = Mt.plane_wave(LAM, MU, RHO, (1, 1, 1), 1, 1.0, "P")
+    Q0 = Bs.project(order, pc, lambda x: f(x, 0.0))
+    cp = np.sqrt((LAM + 2 * MU) / RHO)
+    # the mesh is uniform, so the LARGEST cluster step (4 dt0) has to respect the CFL bound of the cells
+    dt0 = 0.25 * (1.0 / n) / (cp * (2 * order - 1)) / 4
+    macro = int(np.ceil(t_end / (4 * dt0)))
+    dt0 = t_end / (4 * macro)
+    be = NumpyLtsBackend(tab, order, plan, Q0, O.star_dense(star, tab["star_pattern"]), O.flux_dense(ap), O.flux_dense(am))
+    solver = L.LtsSolver(plan, be, order, dt0=dt0)
+    for _ in range(macro):
+        solver.macro_step()
+    ref = np.linalg.norm(Bs.l2_error(order, pc, 0 * Q0, lambda x: f(x, t_end)))
+    err_lts = np.linalg.norm(Bs.l2_error(order, pc, be.Q, lambda x: f(x, t_end))) / ref
+    # global time stepping with dt0 on the same mesh
+    d = {"Q": Q0, "star": star, "Aplus": ap, "Aminus": am, "face_rel": plan.face_rel, "neighbors": plan.neighbors,
+         "face_types": plan.face_types}
+    coeffs = O.time_integrate_coeffs(order, 0.0, dt0)
+    for _ in range(4 * macro):
+        d = O.proxy_step(tab, d, coeffs, "all")
+    err_gts = np.linalg.norm(Bs.l2_error(order, pc, d["Q"], lambda x: f(x, t_end))) / ref
+    assert err_gts < 2e-3
+    assert err_lts < 1.5 * err_gts + 1e-4, (err_lts, err_gts)
