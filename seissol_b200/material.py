@@ -43,6 +43,23 @@ def godunov_state_T(lam, mu, rho, lam_n, mu_n, rho_n):
     return np.eye(9) - god, god
 
 
+def free_surface_godunov_state_T(lam, mu, rho):
+    """getTransposedFreeSurfaceGodunovState (src/Model/Common.h:319-364), elastic: the traction components (0, 3, 5 in
+    the face-aligned frame) are mirrored into the velocities, QgodLocal(t, v) = S(v, t), QgodLocal(v, v) = 1,
+    S = -R21 R11^-1 with the outgoing eigenvectors of the local material."""
+    cp, cs = np.sqrt((lam + 2 * mu) / rho), np.sqrt(mu / rho)
+    r11 = np.diag([lam + 2 * mu, mu, mu])
+    r21 = np.diag([cp, cs, cs])
+    S = -(r21 @ np.linalg.inv(r11))
+    q = np.zeros((9, 9))
+    for col, t in enumerate((0, 3, 5)):
+        for row, v in enumerate((6, 7, 8)):
+            q[t, v] = S[row, col]
+    for v in (6, 7, 8):
+        q[v, v] = 1.0
+    return q
+
+
 def rotation_matrices(n, s, t):
     """getFaceRotationMatrix (ElasticSetup.h:182-198): T and Tinv for the normal / tangent basis."""
     T, Ti = np.zeros((9, 9)), np.zeros((9, 9))
@@ -94,6 +111,8 @@ def cell_local_matrices(coords, neighbors, lam, mu, rho, star_pattern, face_type
             nb = neighbors[e, f]
             m = nb if nb >= 0 else e
             q_loc, q_nb = godunov_state_T(lam[e], mu[e], rho[e], lam[m], mu[m], rho[m])
+            if face_types is not None and face_types[e, f] == 1:          # FaceType::FreeSurface
+                q_loc, q_nb = free_surface_godunov_state_T(lam[e], mu[e], rho[e]), np.zeros((9, 9))
             T, Ti = rotation_matrices(nn, s, t)
             at = coefficient_matrix_T(lam[e], mu[e], rho[e], 0)
             scale = -2.0 * surface / (6.0 * volume)

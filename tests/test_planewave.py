@@ -159,3 +159,57 @@ def test_plane_wave_lts():
     err_gts = np.linalg.norm(Bs.l2_error(order, pc, d["Q"], lambda x: f(x, t_end))) / ref
     assert err_gts < 2e-3
     assert err_lts < 1.5 * err_gts + 1e-4, (err_lts, err_gts)
+
+
+def _shear_pulse_energy(bc_type, order=4, n=6, t_end=0.5):
+    """SH pulse (sigma_xz, u) travelling in +z inside a box: periodic in x, free surface on the y faces, the z faces carry
+    the boundary condition under test.  Returns (E(t_end) / E(0))."""
+    tab = O.load_tables(order, np.float64)
+    m = M.CubeMesh(n, n, n)
+    coords = m.coords / n
+    N = m.n
+    # y faces: traction free (exactly satisfied by this wave, so they do not disturb it; an absorbing boundary would
+    # treat the tangential velocity as an outgoing shear wave and damp it)
+    ft = np.where(m.neighbors < 0, 1, 0).astype(np.uint8)
+    zc = coords[:, M.FACE2NODES, 2]                                             # [N, 4 faces, 3 vertices]
+    on_z = (m.neighbors < 0) & (np.all(zc < 1e-12, axis=2) | np.all(zc > 1 - 1e-12, axis=2))
+    ft[on_z] = bc_type                                                          # ... except the z faces
+    nb = np.where(m.neighbors < 0, np.arange(N)[:, None], m.neighbors)
+    star, ap, am = Mt.cell_local_matrices(coords, m.neighbors, np.full(N, LAM), np.full(N, MU), np.full(N, RHO),
+                                          tab["star_pattern"], ft)
+    cs = np.sqrt(MU / RHO)
+
+    def pulse(x):
+        g = np.exp(-((x[..., 2] - 0.6) / 0.12) ** 2)
+        out = np.zeros(x.shape[:-1] + (9,))
+        out[..., 5] = MU * g          # sigma_xz
+        out[..., 6] = -cs * g         # u: right-going in z
+        return out
+
+    def energy(Q):
+        pts, w = Bs.tet_quadrature(order + 2)
+        phi = Bs.dubiner(order, pts[:, 0], pts[:, 1], pts[:, 2])
+        q = np.einsum("mk,nkq->nmq", phi, Q)
+        jac = np.abs(np.linalg.det(coords[:, 1:] - coords[:, :1]))
+        dens = 0.5 * RHO * (q[..., 6] ** 2 + q[..., 7] ** 2 + q[..., 8] ** 2) + (q[..., 3] ** 2 + q[..., 4] ** 2 + q[..., 5] ** 2) / (2 * MU)
+        return float(np.einsum("n,m,nm->", jac, w, dens))
+
+    d = {"Q": Bs.project(order, coords, pulse), "star": star, "Aplus": ap, "Aminus": am, "face_rel": m.face_rel,
+         "neighbors": nb, "face_types": ft}
+    e0 = energy(d["Q"])
+    cp = np.sqrt((LAM + 2 * MU) / RHO)
+    dt = 0.25 * (1.0 / n) / (cp * (2 * order - 1))
+    steps = int(np.ceil(t_end / dt))
+    coeffs = O.time_integrate_coeffs(order, 0.0, t_end / steps)
+    for _ in range(steps):
+        d = O.proxy_step(tab, d, coeffs, "all")
+    return energy(d["Q"]) / e0
+
+
+def test_free_surface_reflects_and_outflow_absorbs():
+    """Boundary face types only change the local flux solver (material.py): a free surface (FaceType 1) sends the pulse
+    back (energy stays), an absorbing boundary (FaceType 5) lets it leave (energy drops)."""
+    kept = _shear_pulse_energy(1)
+    left = _shear_pulse_energy(5)
+    assert 0.85 < kept < 1.0 + 1e-6, kept      # upwind fluxes dissipate a little, never create energy
+    assert left < 0.15, left
