@@ -213,23 +213,36 @@ class CudaLtsBackend:
             self.perm[c] = t.from_numpy(np.argsort(key, kind="stable").astype(np.int32)).to(dev)
         self.launches = 0
         self.dist = dist
+        self.comm, self.pending = None, set()
         self.send_idx = {c: [(peer, side, t.from_numpy(np.ascontiguousarray(idx)).to(dev)) for peer, side, idx in regs]
                          for c, regs in plan.send.items()}
 
     def exchange(self, c):
         """Halo of cluster c: pack the copy cells' time-integrated DOFs per region (index_select), one NCCL send/recv
-        pair per region, received straight into the ghost rows the neighbor kernel reads."""
-        dist, plan = self.dist, self.plan
-        ops, keep = [], []
-        for peer, side, idx in sorted(self.send_idx[c], key=lambda r: r[1]):
-            buf = self.idofs.index_select(0, idx)
-            keep.append(buf)
-            ops.append(dist.P2POp(dist.isend, buf, peer, tag=2 * c + side))
-        for peer, side, start, count in sorted(plan.recv[c], key=lambda r: 1 - r[1]):
-            ops.append(dist.P2POp(dist.irecv, self.idofs[start:start + count], peer, tag=2 * c + (1 - side)))
-        if ops:
-            for wk in dist.batch_isend_irecv(ops):
-                wk.wait()
+        pair per region, received straight into the ghost rows the neighbor kernel reads.  Runs on a communication
+        stream behind the prediction of cluster c; only the correction of cluster c waits for it, so the predictions
+        and corrections of the other clusters overlap the transfer."""
+        t, dist, plan = self.torch, self.dist, self.plan
+        if self.comm is None:
+            self.comm = t.cuda.Stream(self.idofs.device)
+            self.ev_pred = {k: t.cuda.Event() for k in range(plan.n_clusters)}
+            self.ev_halo = {k: t.cuda.Event() for k in range(plan.n_clusters)}
+        main = t.cuda.current_stream(self.idofs.device)
+        self.ev_pred[c].record(main)
+        with t.cuda.stream(self.comm):
+            self.comm.wait_event(self.ev_pred[c])
+            ops, keep = [], []
+            for peer, side, idx in sorted(self.send_idx[c], key=lambda r: r[1]):
+                buf = self.idofs.index_select(0, idx)
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, peer, tag=2 * c + side))
+            for peer, side, start, count in sorted(plan.recv[c], key=lambda r: 1 - r[1]):
+                ops.append(dist.P2POp(dist.irecv, self.idofs[start:start + count], peer, tag=2 * c + (1 - side)))
+            if ops:
+                for wk in dist.batch_isend_irecv(ops):
+                    wk.wait()
+            self.ev_halo[c].record(self.comm)
+        self.pending.add(c)
 
     def _s(self, x, a, b):
         return self.api.strided(x[a:b])
@@ -257,6 +270,9 @@ class CudaLtsBackend:
 
     def correct(self, c, r, coeffs_full, coeffs_sub):
         ctx, api = self.ctx, self.api
+        if c in self.pending:      # the ghost rows of this cluster must have arrived
+            self.torch.cuda.current_stream(self.idofs.device).wait_event(self.ev_halo[c])
+            self.pending.discard(c)
         for name, coeffs in (("full", coeffs_full), ("sub", coeffs_sub)):
             if (name, c) in self.taylor:
                 src, dst, cnt = self.taylor[(name, c)]
