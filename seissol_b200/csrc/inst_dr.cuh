@@ -51,7 +51,7 @@ int drInterpEntry(DrInterpParams& p, cudaStream_t stream) {
   }
   auto kern = k_dr_interp<Real, GenO, GenDr, NF>;
   p.rawStride = padOdd16(p.derSize, sizeof(Real));
-  const size_t bytes = ((size_t(NF) * (p.rawStride + 84) * sizeof(Real) + 15) / 16) * 16 + 16;
+  const size_t bytes = ((size_t(NF) * (2 * p.rawStride + 84) * sizeof(Real) + 15) / 16) * 16 + 16;
   static size_t configured = 0;
   if (int rc = setSmem(kern, bytes, configured)) {
     return rc;

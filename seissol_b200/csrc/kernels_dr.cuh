@@ -103,13 +103,16 @@ __global__ void __launch_bounds__((DrInterpCfg<R, G, GD, NF>::threads)) k_dr_int
   const int j = active ? tid / NF : 0;  // 0..TPF-1
   const int q = j % 9;
   const int sg = j / 9;
-  R* const raw = smem + f * p.rawStride;
-  R* const tmat = smem + NF * p.rawStride + f * 84;
+  // two derivative buffers per face: the minus side's family is in flight while the plus side is computed
+  R* const raw0 = smem + f * p.rawStride;
+  R* const raw1 = smem + (NF + f) * p.rawStride;
+  R* const tmat = smem + 2 * NF * p.rawStride + f * 84;
   uint64_t* const bar = reinterpret_cast<uint64_t*>(
-      smemRaw + ((size_t(NF) * (p.rawStride + 84) * sizeof(R) + 15) / 16) * 16);
+      smemRaw + ((size_t(NF) * (2 * p.rawStride + 84) * sizeof(R) + 15) / 16) * 16);   // bar[0]: plus, bar[1]: minus
 
   if (tid == 0) {
     mbar_init(bar, NF);
+    mbar_init(bar + 1, NF);
     mbar_fence_init();
   }
   __syncthreads();
@@ -131,18 +134,21 @@ __global__ void __launch_bounds__((DrInterpCfg<R, G, GD, NF>::threads)) k_dr_int
     totalRows += G::derRows(d);
   }
 
+  if (tid < NF) {  // j == 0: this thread moves both derivative families of face f
+    if (face >= 0) {
+      mbar_arrive_expect_tx(bar, p.derSize * sizeof(R));
+      tma_load(raw0, p.derPlus.at(face), p.derSize * sizeof(R), bar);
+      mbar_arrive_expect_tx(bar + 1, p.derSize * sizeof(R));
+      tma_load(raw1, p.derMinus.at(face), p.derSize * sizeof(R), bar + 1);
+    } else {
+      mbar_arrive_expect_tx(bar, 0);
+      mbar_arrive_expect_tx(bar + 1, 0);
+    }
+  }
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
-    if (tid < NF) {  // j == 0: this thread moves the derivative family of face f
-      if (face >= 0) {
-        const ElemArray& src = side == 0 ? p.derPlus : p.derMinus;
-        mbar_arrive_expect_tx(bar, p.derSize * sizeof(R));
-        tma_load(raw, src.at(face), p.derSize * sizeof(R), bar);
-      } else {
-        mbar_arrive_expect_tx(bar, 0);
-      }
-    }
-    mbar_wait(bar, side);
+    R* const raw = side == 0 ? raw0 : raw1;
+    mbar_wait(bar + side, 0);
     __syncthreads();  // (first pass) the face's rotation matrix written above is visible
 
     // ---- rotate every row of every dQ(d) in place: row <- row . TinvT
