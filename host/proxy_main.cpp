@@ -8,7 +8,7 @@
 // Fake data as fakeData (src/Proxy/Allocator.cpp:49-134): per cell and face (side U{0..3}, orientation U{0..2},
 // neighbor U{0..cells-1}) drawn from std::mt19937(cells) in the reference's order; values are bounded
 // instead of fillWithStuff.  --dump writes the inputs and the final DOFs as raw arrays for the parity test
-// (tests/test_gpu_host_cpp.py).  Elastic kernels only: all, local, neigh, ader, localwoader.
+// (tests/test_host_cpp.py).  Kernels: all, local, neigh, ader, localwoader, neigh_dr, godunov_dr, all_dr (elastic).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -28,7 +28,7 @@ using namespace seissol_b200;
 
 namespace {
 
-enum class Kernel { All, Local, Neighbor, Ader, LocalWOAder };
+enum class Kernel { All, Local, Neighbor, Ader, LocalWOAder, NeighborDR, GodunovDR, AllDR };
 
 bool str2kernel(const std::string& s, std::vector<Kernel>& out) {
   std::stringstream ss(s);
@@ -39,6 +39,9 @@ bool str2kernel(const std::string& s, std::vector<Kernel>& out) {
     else if (part == "neigh") out.push_back(Kernel::Neighbor);
     else if (part == "ader") out.push_back(Kernel::Ader);
     else if (part == "localwoader") out.push_back(Kernel::LocalWOAder);
+    else if (part == "neigh_dr") out.push_back(Kernel::NeighborDR);
+    else if (part == "godunov_dr") out.push_back(Kernel::GodunovDR);
+    else if (part == "all_dr") out.push_back(Kernel::AllDR);
     else {
       std::cerr << "Unknown kernel string: " << part << std::endl;
       return false;
@@ -135,9 +138,100 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
     layer.permutation = static_cast<int*>(p);
   }
 
+  // ---- fault-side fake data (src/Proxy/Allocator.cpp:193-294): 4 fault faces per cell, each picking random plus /
+  //      minus cells' derivative families; every cell face maps to a random fault face.  Only for the *_dr kernels.
+  bool needDr = false;
+  for (Kernel k : kernels) {
+    needDr = needDr || k == Kernel::NeighborDR || k == Kernel::GodunovDR || k == Kernel::AllDR;
+  }
+  kernels::FaultLayer fault;
+  if (needDr) {
+    const std::size_t faces = 4 * cells, ders = ctx.derivativesSize();
+    const int pp = ctx.faultPointsPadded();
+    fault.faces = faces;
+    std::vector<real> derivs(cells * ders);
+    std::uniform_real_distribution<double> u01(0.0, 1.0);
+    for (auto& v : derivs) v = static_cast<real>(u01(vrng));
+    void* dDer = nullptr;
+    upload(dDer, derivs);
+    layer.derivatives = dDer;
+    layer.derivativesStride = ders;
+    std::vector<const void*> plus(faces), minus(faces), god(4 * cells), fs(4 * cells);
+    std::vector<std::uint8_t> info(3 * faces), sideRel(8 * cells), drTypes(4 * cells, 3);
+    std::vector<real> tinv(81 * faces), fluxSolver(81 * faces), imposed(faces * 9 * pp);
+    for (auto& v : tinv) v = static_cast<real>(u(vrng));
+    for (auto& v : fluxSolver) v = static_cast<real>(u(vrng) * scale);
+    for (auto& v : imposed) v = static_cast<real>(u(vrng) * scale);
+    void *dTinv = nullptr, *dFs = nullptr, *dImp = nullptr;
+    upload(dTinv, tinv);
+    upload(dFs, fluxSolver);
+    upload(dImp, imposed);
+    std::uniform_int_distribution<std::size_t> faceDist(0, faces - 1);
+    for (std::size_t fc = 0; fc < faces; ++fc) {
+      plus[fc] = static_cast<const char*>(dDer) + cellDist(rng) * ders * sizeof(real);
+      minus[fc] = static_cast<const char*>(dDer) + cellDist(rng) * ders * sizeof(real);
+      info[3 * fc] = static_cast<std::uint8_t>(sideDist(rng));
+      info[3 * fc + 1] = static_cast<std::uint8_t>(sideDist(rng));
+      info[3 * fc + 2] = static_cast<std::uint8_t>(orientationDist(rng));
+    }
+    for (std::size_t c = 0; c < 4 * cells; ++c) {
+      const std::size_t fc = faceDist(rng);
+      god[c] = static_cast<const char*>(dImp) + fc * 9 * pp * sizeof(real);
+      fs[c] = static_cast<const char*>(dFs) + fc * 81 * sizeof(real);
+      sideRel[2 * c] = static_cast<std::uint8_t>(sideDist(rng));
+      sideRel[2 * c + 1] = static_cast<std::uint8_t>(orientationDist(rng));
+    }
+    fault.tinvT = dTinv;
+    upload(p, plus); fault.timeDerivativePlus = static_cast<const void* const*>(p);
+    upload(p, minus); fault.timeDerivativeMinus = static_cast<const void* const*>(p);
+    upload(p, god); fault.godunov = static_cast<const void* const*>(p);
+    upload(p, fs); fault.fluxSolver = static_cast<const void* const*>(p);
+    upload(p, info); fault.faceInformation = static_cast<std::uint8_t*>(p);
+    upload(p, sideRel); fault.sideRelation = static_cast<std::uint8_t*>(p);
+    upload(p, drTypes); fault.drFaceTypes = static_cast<std::uint8_t*>(p);
+    const std::size_t qi = faces * order * 9 * pp;
+    checkCuda(cudaMalloc(&fault.qInterpolatedPlus, qi * sizeof(real)), "cudaMalloc");
+    checkCuda(cudaMalloc(&fault.qInterpolatedMinus, qi * sizeof(real)), "cudaMalloc");
+    // fault faces grouped by their (plus side, minus side, relation) operator variant
+    std::vector<std::pair<int, int>> keyed(faces);
+    for (std::size_t fc = 0; fc < faces; ++fc) {
+      keyed[fc] = {info[3 * fc] + 4 * (info[3 * fc + 1] + 4 * info[3 * fc + 2]), static_cast<int>(fc)};
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<int> fperm(faces);
+    for (std::size_t fc = 0; fc < faces; ++fc) fperm[fc] = keyed[fc].second;
+    upload(p, fperm);
+    fault.permutation = static_cast<int*>(p);
+  }
+
   kernels::Spacetime spacetime(ctx);
   kernels::Local local(ctx);
   kernels::Neighbor neighbor(ctx);
+  kernels::DynamicRupture dynamicRupture(ctx);
+  // Gauss-Legendre points on [0, dt] (src/Numerical/Quadrature.h:76-90) by Newton on the Legendre polynomial; row s of
+  // the coefficient table = tau_s^d / d! (src/Numerical/TimeBasis.h:71-80)
+  std::vector<double> drCoeffs(order * order);
+  for (int s = 0; s < order; ++s) {
+    double x = std::cos(M_PI * (s + 0.75) / (order + 0.5));
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = x;
+      for (int n = 2; n <= order; ++n) {
+        const double pn = ((2.0 * n - 1.0) * x * p1 - (n - 1.0) * p0) / n;
+        p0 = p1;
+        p1 = pn;
+      }
+      const double dp = order * (x * p1 - p0) / (x * x - 1.0);
+      const double dx = p1 / dp;
+      x -= dx;
+      if (std::fabs(dx) < 1e-15) break;
+    }
+    const double tau = 0.5 * 1.0 * (1.0 - x);   // points in ascending order on [0, 1]
+    double f = 1.0;
+    for (int d = 0; d < order; ++d) {
+      if (d > 0) f *= d;
+      drCoeffs[s * order + d] = std::pow(tau, d) / f;
+    }
+  }
   cudaStream_t stream;
   checkCuda(cudaStreamCreate(&stream), "cudaStreamCreate");
   const double dt = 1.0;  // src/Proxy/Constants.h
@@ -147,11 +241,14 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
     fact *= (d + 1);
     coeffs[d] = std::pow(dt, d + 1) / fact;  // MonomialBasis::integrate (src/Numerical/TimeBasis.h:82-96)
   }
+  // all_dr = local, godunov_dr, neigh_dr (src/Proxy/KernelHost.h:29-56); the fault faces replace the regular neighbors
   auto pass = [&]() {
     for (Kernel k : kernels) {
-      if (k == Kernel::All || k == Kernel::Local || k == Kernel::Ader) spacetime.computeBatchedAder(coeffs.data(), dt, layer, stream);
-      if (k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder) local.computeBatchedIntegral(layer, dt, stream);
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::Ader || k == Kernel::AllDR) spacetime.computeBatchedAder(coeffs.data(), dt, layer, stream);
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder || k == Kernel::AllDR) local.computeBatchedIntegral(layer, dt, stream);
       if (k == Kernel::All || k == Kernel::Neighbor) neighbor.computeBatchedNeighborsIntegral(layer, stream);
+      if (k == Kernel::GodunovDR || k == Kernel::AllDR) dynamicRupture.batchedSpaceTimeInterpolation(fault, drCoeffs.data(), stream);
+      if (k == Kernel::NeighborDR || k == Kernel::AllDR) dynamicRupture.computeBatchedNodalFlux(layer, fault, stream);
     }
   };
   pass();  // warm-up pass (Runner.cpp:93-95)
@@ -174,6 +271,11 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
     if (a) { nz += fl.derNz; hw += fl.derHw; reals += 2 * bq + 72; }
     if (l) { nz += fl.volNz + fl.lfNz; hw += fl.volHw + fl.lfHw; reals += 3 * bq + 72 + 324; }
     if (n) { nz += fl.nfNz; hw += fl.nfHw; reals += 6 * bq + 324; }
+    // dynamic rupture, per cell = 4 fault faces (order 6 counts of the generated kernels, SURVEY.md §8: interpolation
+    // 2 x 346 113 per face, nodal flux 56 387 per face on average); all_dr additionally runs the local kernels
+    if (k == Kernel::AllDR) { nz += fl.derNz + fl.volNz + fl.lfNz; hw += fl.derHw + fl.volHw + fl.lfHw; reals += 5 * bq + 144 + 324; }
+    if ((k == Kernel::GodunovDR || k == Kernel::AllDR) && order == 6) { nz += 4 * 692226.0; }
+    if ((k == Kernel::NeighborDR || k == Kernel::AllDR) && order == 6) { nz += 4 * 56387.0; }
   }
   const double total = double(cells) * double(timesteps);
   const double gnz = nz * total * 1e-9, ghw = hw * total * 1e-9, gib = reals * sizeof(real) * total / (1024.0 * 1024.0 * 1024.0);
@@ -229,7 +331,7 @@ int main(int argc, char* argv[]) {
   }
   if (pos.size() != 3) {
     std::cerr << "usage: ssb_proxy <cells> <timesteps> <kernel[,kernel]> [-f plain|json] [--order 4|5|6] [--precision s|d] "
-                 "[--dump PREFIX]\nkernels: all, local, neigh, ader, localwoader" << std::endl;
+                 "[--dump PREFIX]\nkernels: all, local, neigh, ader, localwoader, neigh_dr, godunov_dr, all_dr" << std::endl;
     return -1;
   }
   std::vector<Kernel> kernels;

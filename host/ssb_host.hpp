@@ -45,6 +45,8 @@ class Context {
     ld_ = q[1];
     dofsSize_ = q[2];
     derivativesSize_ = q[3];
+    faultPoints_ = q[22];
+    faultPointsPadded_ = q[23];
   }
   ~Context() { ssb_destroy(ctx_); }
   Context(const Context&) = delete;
@@ -56,10 +58,12 @@ class Context {
   int leadingDimension() const { return ld_; }
   std::size_t dofsSize() const { return dofsSize_; }             // reals per Q / I tensor
   std::size_t derivativesSize() const { return derivativesSize_; }
+  int faultPoints() const { return faultPoints_; }
+  int faultPointsPadded() const { return faultPointsPadded_; }
 
   private:
   ssb_ctx* ctx_{nullptr};
-  int order_, realSize_, basisFunctions_{0}, ld_{0};
+  int order_, realSize_, basisFunctions_{0}, ld_{0}, faultPoints_{0}, faultPointsPadded_{0};
   std::size_t dofsSize_{0}, derivativesSize_{0};
 };
 
@@ -144,6 +148,47 @@ class Neighbor {
                     strided(layer.buffers, layer.dofsStride * rs), strided(layer.neighboringIntegration, 324 * rs),
                     layer.faceTypes, layer.faceRelations, static_cast<long long>(layer.size), layer.permutation, stream),
           "ssb_neigh");
+  }
+
+  private:
+  Context& ctx_;
+};
+
+// Fault-side device arrays of one DynamicRupture::Layer (src/Memory/Descriptor/DynamicRupture.h:47-157) + the
+// CellDRMapping of the adjacent cells (src/Initializer/Typedefs.h:265-270)
+struct FaultLayer {
+  std::size_t faces{0};
+  const void* const* timeDerivativePlus{nullptr};    // [faces] derivative family of the plus-side cell
+  const void* const* timeDerivativeMinus{nullptr};
+  void* tinvT{nullptr};                              // [faces][81]
+  std::uint8_t* faceInformation{nullptr};            // [faces][3] {plusSide, minusSide, faceRelation}
+  void* qInterpolatedPlus{nullptr};                  // [faces][O][9][ppad]
+  void* qInterpolatedMinus{nullptr};
+  int* permutation{nullptr};
+  // per cell and face
+  const void* const* godunov{nullptr};               // [cells][4]
+  const void* const* fluxSolver{nullptr};            // [cells][4]
+  std::uint8_t* sideRelation{nullptr};               // [cells][4][2] {side, faceRelation}
+  std::uint8_t* drFaceTypes{nullptr};                // [cells][4]
+};
+
+class DynamicRupture {
+  public:
+  explicit DynamicRupture(Context& ctx) : ctx_(ctx) {}
+  // src/Kernels/DynamicRupture.h:48-50; coeffs: [O][O] point-evaluation rows (DynamicRupture.cpp:62-70), host array
+  void batchedSpaceTimeInterpolation(FaultLayer& fault, const double* coeffs, cudaStream_t stream) {
+    check(ssb_dr_interp(ctx_.handle(), ssb_array_t{fault.timeDerivativePlus, nullptr, 0},
+                        ssb_array_t{fault.timeDerivativeMinus, nullptr, 0}, fault.tinvT, fault.faceInformation,
+                        fault.qInterpolatedPlus, fault.qInterpolatedMinus, coeffs, static_cast<long long>(fault.faces),
+                        fault.permutation, stream),
+          "ssb_dr_interp");
+  }
+  // DynamicRupture branch of Neighbor::computeBatchedNeighborsIntegral (LinearCK/Neighbor.cpp:150-186)
+  void computeBatchedNodalFlux(Layer& layer, FaultLayer& fault, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_neigh_dr(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), fault.godunov, fault.fluxSolver,
+                       fault.sideRelation, fault.drFaceTypes, static_cast<long long>(layer.size), stream),
+          "ssb_neigh_dr");
   }
 
   private:

@@ -56,3 +56,18 @@ def test_cpp_proxy_matches_oracle(built_library, tmp_path, order, prec, dt, bar)
     for _ in range(steps + 1):      # one warm-up pass + `timesteps` timed passes (src/Proxy/Runner.cpp:93-111)
         d = O.proxy_step(tab, d, coeffs, "all")
     assert rel_l2(modal("_Q.bin"), d["Q"]) < bar
+
+
+@pytest.mark.gpu
+def test_cpp_proxy_dr_kernels_run(built_library):
+    """The dynamic-rupture proxy kernels through the C++ host classes (kernels::DynamicRupture): they run, report the
+    reference proxy's fields and leave finite numbers."""
+    for kernel in ("godunov_dr", "neigh_dr", "all_dr", "local,godunov_dr,neigh_dr"):
+        r = subprocess.run([EXE, "2000", "2", kernel, "--order", "6", "-f", "json"], capture_output=True, text=True)
+        assert r.returncode == 0, (kernel, r.stderr)
+        assert f'"name":"{kernel}"' in r.stdout and '"time":' in r.stdout
+    prefix = "/tmp/ssb_proxy_dr"
+    r = subprocess.run([EXE, "500", "1", "all_dr", "--order", "4", "--dump", prefix], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    q = np.fromfile(prefix + "_Q.bin", dtype=np.float32)
+    assert np.isfinite(q).all() and np.abs(q).max() > 0
