@@ -141,11 +141,12 @@ def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt):
     assert rel_l2(got, want) < step_tol(dt)
 
 
-@pytest.mark.parametrize("order,dt", [(6, np.float32), (6, np.float64), (4, np.float32)])
-def test_all_n_steps(gpu, order, dt):
-    """BASELINE.json parity bar: DOFs after N steps of `all` within 1e-5 (f32) / 1e-11 (f64)."""
+@pytest.mark.parametrize("order,dt,steps", [(6, np.float32, 10), (6, np.float64, 10), (4, np.float32, 10),
+                                            (6, np.float32, 50), (6, np.float64, 50)])
+def test_all_n_steps(gpu, order, dt, steps):
+    """BASELINE.json parity bar: DOFs after N = 10 and N = 50 steps of `all` within 1e-5 (f32) / 1e-11 (f64)."""
     torch, api, proxy = gpu
-    n, steps = 2000, 10
+    n = 2000 if steps == 10 else 600
     ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=21)
     data.sort_by_face_relation()
     k = proxy.ProxyKernels(ctx, data)
