@@ -28,6 +28,25 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+_INCLUDE = __import__("re").compile(r'^\s*#\s*include\s+"([^"]+)"', __import__("re").M)
+
+
+def _includes(path, seen=None):
+    """Files a translation unit depends on: its quoted includes, recursively (so that a change to one kernel family
+    recompiles only the units that use it)."""
+    seen = set() if seen is None else seen
+    try:
+        text = open(path).read()
+    except OSError:
+        return []
+    for inc in _INCLUDE.findall(text):
+        dep = os.path.normpath(os.path.join(os.path.dirname(path), inc))
+        if dep not in seen and os.path.exists(dep):
+            seen.add(dep)
+            _includes(dep, seen)
+    return sorted(seen)
+
+
 def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sources=None):
     """variant: build a differently-configured library libseissol_b200_<variant>.so (development aid for
     A/B measurements; selected at run time with the environment variable SSB_LIB).  Only the translation
@@ -74,7 +93,7 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
 
     for src in sources:
         obj = obj_of(src)
-        if force or _newer(obj, [src] + headers):
+        if force or _newer(obj, [src] + _includes(src)):
             jobs.append((src, obj))
 
     def compile_one(job):

@@ -4,9 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "kernels_elastic.cuh"
-#include "kernels_dr.cuh"
-#include "kernels_visco.cuh"
+#include "params.cuh"
 
 namespace ssb {
 

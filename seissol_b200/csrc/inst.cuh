@@ -2,6 +2,7 @@
 //   SSB_ORDER (4|5|6), SSB_REAL (float|double), SSB_TAG (o6_f32), SSB_E_LOCAL, SSB_E_NEIGH
 // and includes gen/ops_o<SSB_ORDER>.cuh before this header.
 #include "api_internal.h"
+#include "kernels_elastic.cuh"
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)

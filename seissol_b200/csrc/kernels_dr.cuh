@@ -14,70 +14,9 @@
 //                   (src/Kernels/LinearCK/Neighbor.cpp:150-186; dynamicRupture::kernel::nodalFlux).
 #pragma once
 #include "common.cuh"
+#include "params.cuh"
 
 namespace ssb {
-
-struct DrInterpParams {
-  ElemArray derPlus;        // per FACE: derivative family of the plus-side element (DynamicRupture::TimeDerivativePlus)
-  ElemArray derMinus;       // per FACE: minus side
-  const void* tinvT;        // [n][81] DRGodunovData::dataTinvT, column-major TinvT[a + 9 b]
-  const uint8_t* faceInfo;  // [n][3] DRFaceInformation {plusSide, minusSide, faceRelation}
-  void* qPlus;              // [n][O][9][ppad] DynamicRupture::QInterpolatedPlus
-  void* qMinus;
-  const int* perm;
-  long long n;
-  int ppad;
-  int rawStride;            // shared-memory reals per face (>= derSize, odd multiple of 16 bytes)
-  int derSize;
-  int derOffset[8];
-  int derLd[8];
-  double coeffs[8][8];      // [time point][derivative]: tau^d / d!
-};
-
-// FrictionLawData of the reference as a structure of device arrays, all [n][ppad] unless noted
-// (src/Memory/Descriptor/DynamicRupture.h:47-265).
-struct FrictionParams {
-  const void* qPlus;        // [n][O][9][ppad]
-  const void* qMinus;
-  void* imposedPlus;        // [n][9][ppad]
-  void* imposedMinus;
-  const void* impAndEta;    // [n][11]: zp zs zpNeig zsNeig etaP etaS invEtaS invZp invZs invZpNeig invZsNeig
-  const void* initialStress;  // [n][6][ppad]
-  void* mu; void* slip1; void* slip2; void* slipRate1; void* slipRate2; void* slipRateMagnitude;
-  void* accumulatedSlipMagnitude; void* traction1; void* traction2; void* ruptureTime; void* peakSlipRate;
-  void* dynStressTime;
-  uint8_t* ruptureTimePending; uint8_t* dynStressTimePending;
-  // linear slip weakening
-  const void* dC; const void* muS; const void* muD; const void* cohesion; const void* forcedRuptureTime;
-  // rate and state, fast velocity weakening
-  const void* rsA; const void* rsSl0; const void* rsF0; const void* rsMuW; const void* rsB; const void* rsSrW;
-  void* stateVariable; uint8_t* convergenceInner; uint8_t* convergenceOuter;
-  const void* resampleT;    // [P][P]: resampleT[j*P + p] = resample[p][j]
-  long long n;
-  int ppad;
-  double deltaT[8];
-  double timeWeights[8];
-  double fullUpdateTime;
-  double etaPDamp;
-  double healingThreshold;
-  double t0;
-  double rsSr0;
-  double rsSlipRateTolerance;
-  double rsStateTolerance;
-  int rsMaxNumberSlipRateUpdates;
-  int rsNumberStateVariableUpdates;
-};
-
-struct NeighDrParams {
-  ElemArray dofs;
-  const void* const* godunov;      // [n][4] imposed state of the fault face (CellDRMapping::godunov) or null
-  const void* const* fluxSolver;   // [n][4] 9x9 flux solver (CellDRMapping::fluxSolver), column-major [c + 9 q]
-  const uint8_t* sideRel;          // [n][4][2] {side, faceRelation}
-  const uint8_t* faceTypes;        // [n][4]
-  long long n;
-  int ldg;
-  int ppad;
-};
 
 // ---------------------------------------------------------------------------------------
 template <typename R, typename G, typename GD, int NF>

@@ -23,48 +23,9 @@
 // squeezed to two regions per element (4 KB for order 6 / float) so that 16 warps fit.
 #pragma once
 #include "common.cuh"
+#include "params.cuh"
 
 namespace ssb {
-
-// ---------------------------------------------------------------------------------------
-struct LocalParams {
-  ElemArray dofs;      // Q, in/out                         (LTS::Dofs)
-  ElemArray idofs;     // I: out if ader, in if !ader       (LTS::Buffers / Idofs scratch)
-  ElemArray derivs;    // optional derivative family, out   (LTS::Derivatives)
-  ElemArray localInt;  // LocalIntegrationData: star[3][24], nApNm1[4][81]
-  const uint8_t* faceTypes;  // [n][4] FaceType, may be null (= all regular)
-  const int* perm;           // optional processing order
-  long long n;
-  int ldg;             // leading dimension of Q/I columns in global memory (reals)
-  int derOffset[8];    // offset of dQ(d) inside the derivative family (reals)
-  int derLd[8];        // leading dimension of dQ(d) in global memory (reals)
-  double coeffs[8];    // Taylor integration coefficients c_d
-};
-
-struct NeighParams {
-  ElemArray dofs;       // Q in/out
-  ElemArray neighInt;   // NeighboringIntegrationData: nAmNm1[4][81]
-  const void* const* nbPtrs;  // [n][4] pointers to the neighbors' I (LTS::FaceNeighbors) or null
-  const long long* nbIdx;     // else [n][4] indices into idofs
-  ElemArray idofs;
-  const uint8_t* faceTypes;   // [n][4] or null
-  const uint8_t* faceRel;     // [n][4][2] = {neighbor's face j, orientation h}
-  const int* perm;
-  long long n;
-  int ldg;
-};
-
-struct TaylorParams {
-  ElemArray derivs;
-  ElemArray idofs;
-  long long n;
-  int ldg;
-  int order;
-  int rows[8];
-  int derOffset[8];
-  int derLd[8];
-  double coeffs[8];
-};
 
 constexpr int kNQ = 9;
 __host__ __device__ constexpr int blockThreads(int E) { return (kNQ * E + 31) / 32 * 32; }
@@ -734,13 +695,6 @@ __global__ void __launch_bounds__(256) k_taylor(const TaylorParams p) {
 // LTS buffer accumulation: buffers[i] = reset ? idofs[i] : buffers[i] + idofs[i] for cells whose neighbors in a
 // larger time cluster read the sum of two sub-steps (LtsSetup::accumulateBuffers; TimeCluster.cpp:508-530,
 // device::algorithms kernel_streamBatchedData / kernel_accumulateBatchedData).
-struct AccumulateParams {
-  ElemArray buffers;
-  ElemArray idofs;
-  long long n;
-  int vec4PerElem;  // tensor size / 4 reals
-  int reset;
-};
 
 template <typename R>
 __global__ void __launch_bounds__(256) k_lts_accumulate(const AccumulateParams p) {

@@ -23,7 +23,6 @@
 
 namespace ssb {
 
-constexpr int kVM = 3;             // mechanisms
 constexpr int kVNE = 15;           // extended quantities
 constexpr int kVNA = 6 * kVM;      // memory-variable columns
 constexpr int kVStar = 33;
@@ -41,25 +40,6 @@ __device__ constexpr int kVStarRow[15][3] = {{6, 7, 8}, {6, 7, 8}, {6, 7, 8}, {6
                                              {6, 8, 6}};
 __device__ constexpr int kVStarCnt[15] = {3, 3, 3, 2, 2, 2, 3, 3, 3, 1, 1, 1, 2, 2, 2};
 __device__ constexpr int kVStarOff[15] = {0, 3, 6, 9, 11, 13, 15, 18, 21, 24, 25, 26, 27, 29, 31};
-
-struct ViscoLocalParams {
-  ElemArray dofs, dofsAne, idofs, idofsAne, localInt;
-  const uint8_t* faceTypes;
-  long long n;
-  int ldg;
-  double coeffs[8];
-};
-
-struct ViscoNeighParams {
-  ElemArray dofs, dofsAne, idofs, neighInt;
-  const void* const* nbPtrs;
-  const long long* nbIdx;
-  const uint8_t* faceTypes;
-  const uint8_t* faceRel;
-  const int* perm;
-  long long n;
-  int ldg;
-};
 
 template <typename R, typename G, int E>
 struct ViscoPlan {
