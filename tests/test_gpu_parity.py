@@ -241,3 +241,34 @@ def test_linearity_at_full_size(gpu):
     torch.cuda.synchronize()
     diff = (d2.dofs - 2.0 * d1.dofs).double().norm() / d2.dofs.double().norm()
     assert torch.isfinite(diff) and float(diff) < 1e-6
+
+
+def test_entry_points_are_cuda_graph_capture_safe(gpu):
+    """The reference enqueues its device kernels inside CUDA-graph capture (src/Parallel/Runtime/Stream.h:163-190): the
+    entry points must not synchronise or allocate.  Capture `all` (ader, local, neigh) once, replay it, compare with
+    eager launches."""
+    torch, api, proxy = gpu
+    order, dt, n = 6, np.float32, 1500
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=31)
+    data.sort_by_face_relation()
+    k = proxy.ProxyKernels(ctx, data)
+    start = data.dofs.clone()
+    k.all()                                   # warm-up outside the capture (one-time kernel attribute set-up)
+    torch.cuda.synchronize()
+    eager = data.dofs.clone()
+    data.dofs.copy_(start)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            k.all(stream=side)
+    torch.cuda.current_stream().wait_stream(side)
+    data.dofs.copy_(start)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(data.dofs, eager)
+    graph.replay()                            # second replay = second time step
+    torch.cuda.synchronize()
+    host = O.proxy_step(tab, O.proxy_step(tab, host, c, "all"), c, "all")
+    assert rel_l2(data.to_logical(data.dofs), host["Q"]) < run_tol(dt)
