@@ -50,10 +50,29 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
+        # the same macro step captured once into a CUDA graph (the entry points are capture safe) and replayed
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                solver.macro_step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(a.steps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        ms_graph = g0.elapsed_time(g1) / a.steps
+        be.launches = be.launches * a.steps // (a.steps + 1)
         upd = plan.updates_per_macro_step()
         sizes = [r.end - r.start for r in plan.ranges]
         print(f"clusters {ncl}: cells {plan.n} per cluster {sizes} accumulating {plan.n_acc} with derivatives {plan.n_der} "
               f"taylor faces {plan.n_scratch} (setup {setup:.1f} s)")
+        print(f"  macro step as one CUDA graph: {ms_graph:8.3f} ms  {plan.updates_per_macro_step() / ms_graph / 1e3:8.1f} M element-updates/s")
         print(f"  macro step {ms:8.3f} ms  updates/macro step {upd}  {upd / ms / 1e3:8.1f} M element-updates/s  "
               f"launches/macro step {be.launches // a.steps}  finite={bool(torch.isfinite(dofs).all())}")
         if ncl == 1:
