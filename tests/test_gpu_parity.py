@@ -272,3 +272,32 @@ def test_entry_points_are_cuda_graph_capture_safe(gpu):
     torch.cuda.synchronize()
     host = O.proxy_step(tab, O.proxy_step(tab, host, c, "all"), c, "all")
     assert rel_l2(data.to_logical(data.dofs), host["Q"]) < run_tol(dt)
+
+
+def test_invalid_arguments_are_rejected(gpu):
+    """Error behaviour at the boundary: bad arguments return SSB_EINVAL (-1) before anything is launched; the DOFs stay
+    untouched."""
+    import ctypes
+    torch, api, proxy = gpu
+    ctx = api.Context(6, 4)
+    lib = ctx.lib
+    d = proxy.ProxyData.synthetic(ctx, 64)
+    before = d.dofs.clone()
+    coeffs = (ctypes.c_double * 6)(*[1.0] * 6)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ok, none = api.strided(d.dofs), api.NONE
+    assert lib.ssb_ader(ctx.handle, none, api.strided(d.buffers), none, api.strided(d.local_int), coeffs, 64, None, s) == -1
+    assert lib.ssb_ader(ctx.handle, ok, api.strided(d.buffers), none, api.strided(d.local_int), None, 64, None, s) == -1
+    assert lib.ssb_ader(ctx.handle, ok, api.strided(d.buffers), none, api.strided(d.local_int), coeffs, -5, None, s) == -1
+    assert lib.ssb_local(ctx.handle, ok, none, api.strided(d.local_int), None, 64, None, s) == -1
+    assert lib.ssb_neigh(ctx.handle, ok, None, None, api.strided(d.buffers), api.strided(d.neigh_int), None,
+                         ctypes.c_void_p(d.face_rel.data_ptr()), 64, None, s) == -1          # neither pointers nor indices
+    assert lib.ssb_neigh(ctx.handle, ok, None, ctypes.c_void_p(d.neighbors.data_ptr()), api.strided(d.buffers),
+                         api.strided(d.neigh_int), None, None, 64, None, s) == -1              # no face relations
+    assert lib.ssb_set_layout(ctx.handle, 54, None, None) == -1                                # ld not a multiple of 4
+    assert lib.ssb_set_layout(ctx.handle, 52, None, None) == -1                                # ld < padded basis size
+    assert lib.ssb_visco_ader(ctx.handle, ok, ok, ok, ok, ok, coeffs, 64, s) == -1             # elastic context
+    assert lib.ssb_lts_accumulate(ctx.handle, none, ok, 1, 64, s) == -1
+    torch.cuda.synchronize()
+    assert torch.equal(before, d.dofs)
+    assert b"invalid" in lib.ssb_error_string(-1)
