@@ -1,4 +1,8 @@
 // Kernel instantiation: elastic, order 4, float.
+// resident CTAs per SM the registers are sized for: the order-4 columns are short, 4 CTAs (= 32 warps) per SM
+// measured best (profiles/r1_other_orders_quick_bench.txt)
+#define SSB_MINB_LOCAL 4
+#define SSB_MINB_NEIGH 4
 #include "gen/ops_o4.cuh"
 #define SSB_ORDER 4
 #define SSB_REAL float

@@ -1,4 +1,8 @@
 // Kernel instantiation: elastic, order 5, float.
+// resident CTAs per SM the registers are sized for: the order-5 columns are short, 3 CTAs (= 24 warps) per SM
+// measured best (profiles/r1_other_orders_quick_bench.txt)
+#define SSB_MINB_LOCAL 3
+#define SSB_MINB_NEIGH 3
 #include "gen/ops_o5.cuh"
 #define SSB_ORDER 5
 #define SSB_REAL float
