@@ -213,3 +213,54 @@ def test_free_surface_reflects_and_outflow_absorbs():
     left = _shear_pulse_energy(5)
     assert 0.85 < kept < 1.0 + 1e-6, kept      # upwind fluxes dissipate a little, never create energy
     assert left < 0.15, left
+
+
+POINTS = np.array([[0.31, 0.42, 0.53], [0.77, 0.15, 0.6], [0.05, 0.93, 0.21]])
+
+
+def test_receivers_follow_the_plane_wave():
+    """Receivers (seissol_b200/receiver.py) sample the predictor's Taylor expansion inside every step: the time series at
+    three points follow the exact plane wave."""
+    from seissol_b200 import receiver as Rc
+    order, n, t_end = 4, 8, 0.04
+    tab, coords, f, d, dt = setup(order, n, "P")
+    steps = int(np.ceil(t_end / dt))
+    dt = t_end / steps
+    coeffs = O.time_integrate_coeffs(order, 0.0, dt)
+    rc = Rc.ReceiverCluster(order, coords, POINTS, sampling_interval=dt / 3)
+    star = O.star_dense(d["star"], tab["star_pattern"])
+    for s in range(steps):
+        _, ders = O.ader(tab, d["Q"][rc.elements], star[rc.elements], coeffs, True)
+        rc.step(ders, s * dt, dt)
+        d = O.proxy_step(tab, d, coeffs, "all")
+    times, series = rc.series()
+    assert len(times) == 3 * steps and abs(times[1] - dt / 3) < 1e-15
+    exact = np.stack([f(POINTS, t) for t in times], 1)
+    assert rel_l2(series, exact) < 5e-3
+
+
+@pytest.mark.gpu
+def test_receivers_cuda(built_library):
+    """Same receivers with the CUDA kernels: the derivative families of the receiver elements come from `ssb_ader` on a
+    pointer-table batch of three elements."""
+    import torch
+    from seissol_b200 import api, proxy
+    from seissol_b200 import receiver as Rc
+    order, n, t_end, dtp = 4, 8, 0.04, np.float64
+    tab, coords, f, d, dt = setup(order, n, "P", dtp)
+    steps = int(np.ceil(t_end / dt))
+    dt = t_end / steps
+    coeffs = O.time_integrate_coeffs(order, 0.0, dt, dtp)
+    ctx = api.Context(order, 8)
+    data = proxy.ProxyData.from_host(ctx, d)
+    data.sort_by_face_relation()
+    k = proxy.ProxyKernels(ctx, data)
+    k.coeffs = coeffs
+    rc = Rc.ReceiverCluster(order, coords, POINTS, sampling_interval=dt / 3)
+    for s in range(steps):
+        rc.step(Rc.receiver_derivatives_cuda(torch, api, ctx, data, rc.elements, coeffs), s * dt, dt)
+        k.all()
+    torch.cuda.synchronize()
+    times, series = rc.series()
+    exact = np.stack([f(POINTS, t) for t in times], 1)
+    assert rel_l2(series, exact) < 5e-3
