@@ -335,6 +335,7 @@ int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* 
   p.n = n;
   p.ldg = c->ldq;
   p.order = c->order;
+  p.derSize = c->derSize;
   for (int d = 0; d < c->order; ++d) {
     p.rows[d] = basisFunctions(c->order - d);
     p.derOffset[d] = c->derOffset[d];

@@ -134,12 +134,16 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
-  const long long total = p.n * kNQ * ((p.rows[0] + 3) / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 32) {
-    blocks = 148LL * 32;
+  const size_t bytes = (size_t(kTaylorE) * (p.derSize + kNQ * p.ldg) * sizeof(Real) + 15) / 16 * 16 + 16;
+  static size_t configured = 0;
+  if (bytes > configured) {
+    cudaError_t err = cudaFuncSetAttribute(k_taylor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (err != cudaSuccess) {
+      return int(err);
+    }
+    configured = bytes;
   }
-  k_taylor<Real><<<unsigned(blocks), 256, 0, stream>>>(p);
+  k_taylor<Real><<<unsigned((p.n + kTaylorE - 1) / kTaylorE), 256, bytes, stream>>>(p);
   return int(cudaGetLastError());
 }
 

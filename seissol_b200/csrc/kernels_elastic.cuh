@@ -663,31 +663,65 @@ __global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_NEIGH) k_neigh(cons
 }
 
 // ---------------------------------------------------------------------------------------
-// Taylor sum I = sum_d c_d dQ(d): pure streaming, one thread per (element, column, 4 rows).
+// Taylor sum I = sum_d c_d dQ(d): pure streaming (1 638 reals moved per 1 764 flop at order 6).  The derivative family
+// of an element is one contiguous block and I another, so both cross the SM boundary as 1-D TMA bulk copies (fully
+// coalesced whatever the row counts of the dQ(d) are); the sum itself reads shared memory.  A CTA owns E elements.
+constexpr int kTaylorE = 4;
 template <typename R>
 __global__ void __launch_bounds__(256) k_taylor(const TaylorParams p) {
-  const int vecPerCol = (p.rows[0] + 3) / 4;
-  const long long total = p.n * kNQ * vecPerCol;
-  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const long long el = i / (kNQ * vecPerCol);
-    const int rem = static_cast<int>(i - el * (kNQ * vecPerCol));
+  constexpr int E = kTaylorE;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  R* const smem = reinterpret_cast<R*>(smemRaw);
+  const int tenI = kNQ * p.ldg;
+  const int per = p.derSize + tenI;                      // reals per element: family | I
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + (size_t(E) * per * sizeof(R) + 15) / 16 * 16);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, E);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long first = static_cast<long long>(blockIdx.x) * E;
+  if (tid < E) {
+    const long long el = first + tid;
+    if (el < p.n) {
+      mbar_arrive_expect_tx(bar, p.derSize * sizeof(R));
+      tma_load(smem + tid * per, p.derivs.at(el), p.derSize * sizeof(R), bar);
+    } else {
+      mbar_arrive_expect_tx(bar, 0);
+    }
+  }
+  mbar_wait(bar, 0);
+  const int vecPerCol = p.ldg / 4;
+  const int items = E * kNQ * vecPerCol;
+  for (int i = tid; i < items; i += 256) {
+    const int e = i / (kNQ * vecPerCol);
+    const int rem = i - e * (kNQ * vecPerCol);
     const int c = rem / vecPerCol;
     const int k0 = 4 * (rem - c * vecPerCol);
-    const R* der = static_cast<const R*>(p.derivs.at(el));
+    const R* der = smem + e * per;
     R out[4] = {R(0), R(0), R(0), R(0)};
-    for (int d = 0; d < p.order; ++d) {
-      if (k0 < p.rows[d]) {
-        R t[4];
-        ld4(t, der + p.derOffset[d] + c * p.derLd[d] + k0);
-        const R cd = static_cast<R>(p.coeffs[d]);
+    if (first + e < p.n) {
+      for (int d = 0; d < p.order; ++d) {
+        if (k0 < p.rows[d]) {
+          R t[4];
+          ld4(t, der + p.derOffset[d] + c * p.derLd[d] + k0);
+          const R cd = static_cast<R>(p.coeffs[d]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          out[j] = (k0 + j < p.rows[d]) ? fma(cd, t[j], out[j]) : out[j];
+          for (int j = 0; j < 4; ++j) {
+            out[j] = (k0 + j < p.rows[d]) ? fma(cd, t[j], out[j]) : out[j];
+          }
         }
       }
     }
-    R* dst = static_cast<R*>(const_cast<void*>(p.idofs.at(el))) + c * p.ldg + k0;
-    st4(dst, out[0], out[1], out[2], out[3]);
+    st4(smem + e * per + p.derSize + c * p.ldg + k0, out[0], out[1], out[2], out[3]);
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (tid < E && first + tid < p.n) {
+    tma_store(const_cast<void*>(p.idofs.at(first + tid)), smem + tid * per + p.derSize, tenI * sizeof(R));
+    tma_store_commit();
+    tma_store_wait_read();
   }
 }
 

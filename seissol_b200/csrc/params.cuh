@@ -41,6 +41,7 @@ struct TaylorParams {
   long long n;
   int ldg;
   int order;
+  int derSize;  // reals of one derivative family (contiguous per element)
   int rows[8];
   int derOffset[8];
   int derLd[8];
