@@ -6,13 +6,10 @@ steps=${@:-"test qb bench ncu"}
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/env.txt 2>&1
-PK2=$PWD/seissol_b200/lib/libseissol_b200_pk2.so
 for s in $steps; do
 case $s in
 test)
   timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "exit $?" >> $out/pytest.log ;;
-testpk2)
-  SSB_LIB=$PK2 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "6" > $out/pytest_pk2.log 2>&1; echo "exit $?" >> $out/pytest_pk2.log ;;
 v4)
   NP7=$PWD/seissol_b200/lib/libseissol_b200_np7.so
   SSB_KGEN=4 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_v4.log 2>&1; echo "exit $?" >> $out/pytest_v4.log
@@ -60,8 +57,6 @@ ubench)
 qb)
   timeout 300 python tools/quick_bench.py > $out/qb.txt 2>&1
   SSB_PERSISTENT=2 timeout 300 python tools/quick_bench.py > $out/qb_persist2.txt 2>&1
-  [ -f $PK2 ] && SSB_LIB=$PK2 timeout 300 python tools/quick_bench.py > $out/qb_pk2.txt 2>&1
-  [ -f $PK2 ] && SSB_PERSISTENT=1 SSB_LIB=$PK2 timeout 300 python tools/quick_bench.py > $out/qb_pk2_persist1.txt 2>&1
   timeout 300 python tools/quick_bench.py --real 8 --cells 500000 > $out/qb_f64.txt 2>&1 ;;
 qbdr)
   timeout 300 python tools/quick_bench_dr.py > $out/qbdr.txt 2>&1
