@@ -314,24 +314,131 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
   return 0;
 }
 
+// viscoelastic2, order 5, 3 mechanisms (BASELINE.json configs[2]): same protocol on the anelastic kernel classes
+template <typename real>
+int runVisco(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& kernels, const std::string& kernelStr, bool json,
+             const std::string& dump) {
+  const int order = 5;
+  Context ctx(order, sizeof(real), false, 1, 3);
+  const int B = ctx.basisFunctions(), ld = ctx.leadingDimension();
+  const std::size_t qs = ctx.dofsSize(), as = 18 * static_cast<std::size_t>(ld);
+  std::mt19937 rng(static_cast<unsigned>(cells));
+  std::uniform_int_distribution<unsigned> sideDist(0, 3), orientationDist(0, 2);
+  std::uniform_int_distribution<std::size_t> cellDist(0, cells - 1);
+  std::vector<std::uint8_t> faceTypes(4 * cells, 0), faceRel(8 * cells);
+  std::vector<long long> neighbors(4 * cells);
+  for (std::size_t c = 0; c < cells; ++c) {
+    for (int f = 0; f < 4; ++f) {
+      faceRel[8 * c + 2 * f] = static_cast<std::uint8_t>(sideDist(rng));
+      faceRel[8 * c + 2 * f + 1] = static_cast<std::uint8_t>(orientationDist(rng));
+      neighbors[4 * c + f] = static_cast<long long>(cellDist(rng));
+    }
+  }
+  std::mt19937 vrng(43);
+  std::uniform_real_distribution<double> u(-1.0, 1.0);
+  const double scale = 1e-2;
+  std::vector<real> dofs(cells * qs, real(0)), ane(cells * as, real(0)), localInt(cells * 807), neighInt(cells * 543);
+  for (std::size_t c = 0; c < cells; ++c) {
+    for (int q = 0; q < 9; ++q)
+      for (int k = 0; k < B; ++k) dofs[c * qs + q * ld + k] = static_cast<real>(u(vrng));
+    for (int q = 0; q < 18; ++q)
+      for (int k = 0; k < B; ++k) ane[c * as + q * ld + k] = static_cast<real>(u(vrng));
+  }
+  for (auto& v : localInt) v = static_cast<real>(u(vrng) * scale);
+  for (auto& v : neighInt) v = static_cast<real>(u(vrng) * scale);
+  kernels::ViscoLayer layer;
+  layer.size = cells;
+  layer.realSize = sizeof(real);
+  layer.dofsStride = qs;
+  layer.aneStride = as;
+  upload(layer.dofs, dofs);
+  upload(layer.dofsAne, ane);
+  std::vector<real> zq(cells * qs, real(0)), za(cells * as, real(0));
+  upload(layer.buffers, zq);
+  upload(layer.buffersAne, za);
+  upload(layer.localIntegration, localInt);
+  upload(layer.neighboringIntegration, neighInt);
+  void* p = nullptr;
+  upload(p, faceTypes); layer.faceTypes = static_cast<std::uint8_t*>(p);
+  upload(p, faceRel); layer.faceRelations = static_cast<std::uint8_t*>(p);
+  upload(p, neighbors); layer.faceNeighbors = static_cast<long long*>(p);
+  kernels::anelastic::Spacetime spacetime(ctx);
+  kernels::anelastic::Local local(ctx);
+  kernels::anelastic::Neighbor neighbor(ctx);
+  cudaStream_t stream;
+  checkCuda(cudaStreamCreate(&stream), "cudaStreamCreate");
+  std::vector<double> coeffs(order);
+  double fact = 1.0;
+  for (int d = 0; d < order; ++d) {
+    fact *= (d + 1);
+    coeffs[d] = 1.0 / fact;
+  }
+  auto pass = [&]() {
+    for (Kernel k : kernels) {
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::Ader) spacetime.computeBatchedAder(coeffs.data(), 1.0, layer, stream);
+      if (k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder) local.computeBatchedIntegral(layer, 1.0, stream);
+      if (k == Kernel::All || k == Kernel::Neighbor) neighbor.computeBatchedNeighborsIntegral(layer, stream);
+    }
+  };
+  pass();
+  checkCuda(cudaStreamSynchronize(stream), "sync");
+  const auto t0 = std::chrono::steady_clock::now();
+  for (std::size_t t = 0; t < timesteps; ++t) pass();
+  checkCuda(cudaStreamSynchronize(stream), "sync");
+  const double time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  double nz = 0;   // kernel::X::NonZeroFlops of the generated viscoelastic2 kernels (order 5, 3 mechanisms)
+  for (Kernel k : kernels) {
+    if (k == Kernel::All || k == Kernel::Local || k == Kernel::Ader) nz += 120489;
+    if (k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder) nz += 15924 + 67680 + 14175;
+    if (k == Kernel::All || k == Kernel::Neighbor) nz += 4 * 17511.0 + 1575;
+  }
+  const double total = double(cells) * double(timesteps);
+  if (json) {
+    std::cout << "{\"name\":\"" << kernelStr << "\",\"equations\":\"viscoelastic2\",\"time\":" << time << ",\"cycles\":0,\"gflop-nz\":"
+              << nz * total * 1e-9 << ",\"gflops-nz\":" << nz * total * 1e-9 / time << ",\"elem-updates-per-s\":" << total / time << "}\n";
+  } else {
+    std::cout << "seissol proxy mode                  : " << kernelStr << " (viscoelastic2)\n"
+              << "time for seissol proxy              : " << time << "\n"
+              << "GFLOPS (non-zero) for seissol proxy : " << nz * total * 1e-9 / time << "\n"
+              << "element updates/s                   : " << total / time << "\n";
+  }
+  if (!dump.empty()) {
+    std::vector<real> out(cells * qs), outA(cells * as);
+    checkCuda(cudaMemcpy(out.data(), layer.dofs, out.size() * sizeof(real), cudaMemcpyDeviceToHost), "cudaMemcpy");
+    checkCuda(cudaMemcpy(outA.data(), layer.dofsAne, outA.size() * sizeof(real), cudaMemcpyDeviceToHost), "cudaMemcpy");
+    dumpRaw(dump + "_Q0.bin", dofs);
+    dumpRaw(dump + "_Qane0.bin", ane);
+    dumpRaw(dump + "_Q.bin", out);
+    dumpRaw(dump + "_Qane.bin", outA);
+    dumpRaw(dump + "_localInt.bin", localInt);
+    dumpRaw(dump + "_neighInt.bin", neighInt);
+    dumpRaw(dump + "_faceRel.bin", faceRel);
+    dumpRaw(dump + "_neighbors.bin", neighbors);
+    std::ofstream meta(dump + "_meta.txt");
+    meta << cells << ' ' << timesteps << ' ' << order << ' ' << sizeof(real) << ' ' << B << ' ' << ld << '\n';
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char* argv[]) {
   std::vector<std::string> pos;
   bool json = false;
   int order = 6;
-  std::string precision = "s", dump;
+  std::string precision = "s", dump, equations = "elastic";
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if ((a == "-f" || a == "--format") && i + 1 < argc) json = std::string(argv[++i]) == "json";
     else if (a == "--order" && i + 1 < argc) order = std::atoi(argv[++i]);
     else if (a == "--precision" && i + 1 < argc) precision = argv[++i];
     else if (a == "--dump" && i + 1 < argc) dump = argv[++i];
+    else if (a == "--equations" && i + 1 < argc) equations = argv[++i];
     else pos.push_back(a);
   }
   if (pos.size() != 3) {
     std::cerr << "usage: ssb_proxy <cells> <timesteps> <kernel[,kernel]> [-f plain|json] [--order 4|5|6] [--precision s|d] "
-                 "[--dump PREFIX]\nkernels: all, local, neigh, ader, localwoader, neigh_dr, godunov_dr, all_dr" << std::endl;
+                 "[--dump PREFIX] [--equations elastic|viscoelastic2]\nkernels: all, local, neigh, ader, localwoader, neigh_dr, godunov_dr, all_dr" << std::endl;
     return -1;
   }
   std::vector<Kernel> kernels;
@@ -340,6 +447,16 @@ int main(int argc, char* argv[]) {
   }
   try {
     const std::size_t cells = std::stoull(pos[0]), timesteps = std::stoull(pos[1]);
+    if (equations == "viscoelastic2") {
+      for (Kernel k : kernels) {
+        if (k == Kernel::NeighborDR || k == Kernel::GodunovDR || k == Kernel::AllDR) {
+          std::cerr << "ssb_proxy: the dynamic-rupture kernels are built for the elastic equations" << std::endl;
+          return -1;
+        }
+      }
+      return precision == "d" ? runVisco<double>(cells, timesteps, kernels, pos[2], json, dump)
+                              : runVisco<float>(cells, timesteps, kernels, pos[2], json, dump);
+    }
     if (precision == "d") {
       return run<double>(cells, timesteps, kernels, pos[2], order, json, dump);
     }

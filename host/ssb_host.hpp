@@ -34,8 +34,9 @@ inline void checkCuda(cudaError_t e, const char* what) {
 // One (ConvergenceOrder, real, equation) configuration (the reference builds one binary per configuration).
 class Context {
   public:
-  Context(int order, int realSize, bool referenceLayout = false) : order_(order), realSize_(realSize) {
-    check(ssb_create(&ctx_, order, realSize, 0, 0), "ssb_create");
+  Context(int order, int realSize, bool referenceLayout = false, int equation = 0, int mechanisms = 0)
+      : order_(order), realSize_(realSize) {
+    check(ssb_create(&ctx_, order, realSize, equation, mechanisms), "ssb_create");
     if (referenceLayout) {
       check(ssb_layout_reference(ctx_), "ssb_layout_reference");
     }
@@ -153,6 +154,61 @@ class Neighbor {
   private:
   Context& ctx_;
 };
+
+// viscoelastic2 (src/Kernels/LinearCKAnelastic/*): the same layer plus the memory variables (LTS::DofsAne) and their time
+// integral; localIntegration = star[3][33] | nApNm1[4][135] | E[162] | w[3] | W[3], neighboringIntegration =
+// nAmNm1[4][135] | w[3] (src/Equations/viscoelastic2/Model/IntegrationData.h)
+struct ViscoLayer : Layer {
+  void* dofsAne{nullptr};
+  void* buffersAne{nullptr};        // LocalTmp::timeIntegratedAne of the reference, per cell
+  std::size_t aneStride{0};         // reals per cell
+};
+
+namespace anelastic {
+class Spacetime {
+  public:
+  explicit Spacetime(Context& ctx) : ctx_(ctx) {}
+  void computeBatchedAder(const double* coeffs, double, ViscoLayer& l, cudaStream_t stream) {
+    const std::size_t rs = l.realSize;
+    check(ssb_visco_ader(ctx_.handle(), strided(l.dofs, l.dofsStride * rs), strided(l.dofsAne, l.aneStride * rs),
+                         strided(l.buffers, l.dofsStride * rs), strided(l.buffersAne, l.aneStride * rs),
+                         strided(l.localIntegration, 807 * rs), coeffs, static_cast<long long>(l.size), stream),
+          "ssb_visco_ader");
+  }
+
+  private:
+  Context& ctx_;
+};
+class Local {
+  public:
+  explicit Local(Context& ctx) : ctx_(ctx) {}
+  void computeBatchedIntegral(ViscoLayer& l, double, cudaStream_t stream) {
+    const std::size_t rs = l.realSize;
+    check(ssb_visco_local(ctx_.handle(), strided(l.dofs, l.dofsStride * rs), strided(l.dofsAne, l.aneStride * rs),
+                          strided(l.buffers, l.dofsStride * rs), strided(l.buffersAne, l.aneStride * rs),
+                          strided(l.localIntegration, 807 * rs), l.faceTypes, static_cast<long long>(l.size), stream),
+          "ssb_visco_local");
+  }
+
+  private:
+  Context& ctx_;
+};
+class Neighbor {
+  public:
+  explicit Neighbor(Context& ctx) : ctx_(ctx) {}
+  void computeBatchedNeighborsIntegral(ViscoLayer& l, cudaStream_t stream) {
+    const std::size_t rs = l.realSize;
+    check(ssb_visco_neigh(ctx_.handle(), strided(l.dofs, l.dofsStride * rs), strided(l.dofsAne, l.aneStride * rs),
+                          l.faceNeighborPtrs, l.faceNeighbors, strided(l.buffers, l.dofsStride * rs),
+                          strided(l.neighboringIntegration, 543 * rs), l.faceTypes, l.faceRelations,
+                          static_cast<long long>(l.size), l.permutation, stream),
+          "ssb_visco_neigh");
+  }
+
+  private:
+  Context& ctx_;
+};
+}  // namespace anelastic
 
 // Fault-side device arrays of one DynamicRupture::Layer (src/Memory/Descriptor/DynamicRupture.h:47-157) + the
 // CellDRMapping of the adjacent cells (src/Initializer/Typedefs.h:265-270)
