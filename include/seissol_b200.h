@@ -101,6 +101,27 @@ int ssb_neigh(ssb_ctx* ctx, ssb_array_t dofs, const void* const* nb_ptrs, const 
               ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types,
               const uint8_t* face_rel, long long n, const int* perm, void* stream);
 
+/* Face-projection path of the neighbor flux (GTS, or LTS neighbors of the same cluster).
+ * The face mass matrix of the reference element is diagonal and the same on all four faces (fMrT_f = D rT_f,
+ * codegen/matrices/matrices_*.xml), so the local kernel already holds F_f = fMrT_f I = D (rT_f I) for every face f of
+ * its element while it evaluates the local flux (codegen/kernels/aderdg.py:373-385).  ssb_local_faceproj /
+ * ssb_ader_local_faceproj additionally store these four [9][B2P] blocks per element (face_proj: 4*9*B2P reals per
+ * element, B2P = O(O+1)/2 padded to 4; entries of faces with FaceType DynamicRupture are written as well), and
+ * ssb_neigh_faceproj evaluates  Q_i += rDivM_i (fP_h D^-1) (F_j,nb AminusT_i)  from the block of face j of each
+ * neighbor: 4 x 864 B gathered per element instead of 4 x 2016 B (order 6, float) and no rT_j products.
+ * Same result as ssb_local + ssb_neigh (src/Kernels/LinearCK/Neighbor.cpp:111-188) up to rounding.
+ * nb_idx: device [n][4] indices into face_proj; or nb_ptrs: device [n][4] pointers to the NEIGHBOR's face_proj block
+ * (NULL entry = face contributes nothing).  The pointers must be 16-byte aligned. */
+int ssb_local_faceproj(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t local_int,
+                       ssb_array_t face_proj, const uint8_t* face_types, long long n, const int* perm,
+                       void* stream);
+int ssb_ader_local_faceproj(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs,
+                            ssb_array_t local_int, ssb_array_t face_proj, const uint8_t* face_types,
+                            const double* coeffs, long long n, const int* perm, void* stream);
+int ssb_neigh_faceproj(ssb_ctx* ctx, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
+                       ssb_array_t face_proj, ssb_array_t neigh_int, const uint8_t* face_types,
+                       const uint8_t* face_rel, long long n, const int* perm, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dynamic rupture.  Fault tensors use the reference's layout: point index fastest, padded to
  * `ppad` points (default: multiple of 4; ssb_layout_reference: 64-byte aligned like

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(HERE, "lib", "libseissol_b2
 SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",
     "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_lts_accumulate", "ssb_neigh",
+    "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh",
     "ssb_error_string", "ssb_version",
@@ -80,6 +81,9 @@ def load_library():
     lib.ssb_taylor.argtypes = [P, A, A, P, LL, P]
     lib.ssb_neigh.argtypes = [P, A, P, P, A, A, P, P, LL, P, P]
     lib.ssb_lts_accumulate.argtypes = [P, A, A, I, LL, P]
+    lib.ssb_local_faceproj.argtypes = [P, A, A, A, A, P, LL, P, P]
+    lib.ssb_ader_local_faceproj.argtypes = [P, A, A, A, A, A, P, P, LL, P, P]
+    lib.ssb_neigh_faceproj.argtypes = [P, A, P, P, A, A, P, P, LL, P, P]
     lib.ssb_set_dr_layout.argtypes = [P, I]
     lib.ssb_dr_interp.argtypes = [P, A, A, P, P, P, P, P, LL, P, P]
     lib.ssb_friction_lsw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
@@ -182,6 +186,29 @@ class Context:
               perm=None, stream=None):
         _check(self.lib.ssb_neigh(self.handle, dofs, _ptr(nb_ptrs), _ptr(nb_idx), idofs, neigh_int,
                                   _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
+
+    # -- face-projection path (include/seissol_b200.h) -------------------------------------------
+    def face_proj_reals(self):
+        """reals per element of the face-projection array: [4][9][B2P]."""
+        b2 = self.order * (self.order + 1) // 2
+        return 4 * 9 * ((b2 + 3) // 4 * 4)
+
+    def local_faceproj(self, dofs, idofs, local_int, face_proj, face_types, n, perm=None, stream=None):
+        _check(self.lib.ssb_local_faceproj(self.handle, dofs, idofs, local_int, face_proj, _ptr(face_types), n,
+                                           _ptr(perm), _stream(stream)))
+
+    def ader_local_faceproj(self, dofs, idofs, derivs, local_int, face_proj, face_types, coeffs, n, perm=None,
+                            stream=None):
+        keep, c = self._coeffs(coeffs)
+        _check(self.lib.ssb_ader_local_faceproj(self.handle, dofs, idofs, derivs if derivs is not None else NONE,
+                                                local_int, face_proj, _ptr(face_types), c, n, _ptr(perm),
+                                                _stream(stream)))
+
+    def neigh_faceproj(self, dofs, face_proj, neigh_int, face_types, face_rel, n, nb_idx=None, nb_ptrs=None,
+                       perm=None, stream=None):
+        _check(self.lib.ssb_neigh_faceproj(self.handle, dofs, _ptr(nb_ptrs), _ptr(nb_idx),
+                                           face_proj if face_proj is not None else NONE, neigh_int,
+                                           _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
 
     # -- viscoelastic2 --------------------------------------------------------------------------
     def visco_ader(self, dofs, dofs_ane, idofs, idofs_ane, local_int, coeffs, n, stream=None):

@@ -54,8 +54,15 @@ class Emitter:
         return "\n".join(self.lines) + "\n"
 
 
+LS_PERIOD = 64   # a lock-step marker SSB_LS(i) every LS_PERIOD FMAs (common.cuh decides whether it is a barrier)
+
+
 def emit_acc(em, touched, name, k, coef, operand):
     """acc[k] (+)= coef*operand; first touch of a zero-initialised output is a plain mul."""
+    if getattr(em, "lockstep", False):
+        em.nacc = getattr(em, "nacc", 0) + 1
+        if em.nacc % LS_PERIOD == 0:
+            em.w(f"  SSB_LS({em.nacc // LS_PERIOD});")
     if touched is not None and k not in touched:
         touched.add(k)
         em.w(f"  {name}[{k}] = pk_mulc({lit(coef)}, {operand});")
@@ -67,6 +74,7 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
     """out[k] (+)= sum_j sum_l M_j[k,l] * t_j[l],  t_j[l] = sum_{c<3} s[j][c] * a_c[l]
     where a_c = column r_c of the source tensor (pointers a0,a1,a2 in shared memory).
     mats: list of 3 dense matrices (already restricted to [rows_out, rows_in])."""
+    em.lockstep, em.nacc = True, 0
     em.w("template <typename R>")
     em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const R* __restrict__ a0,"
          " const R* __restrict__ a1, const R* __restrict__ a2, const typename Pk<R>::T (&s)[3][3]) {")
@@ -102,9 +110,10 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, out_pad, accumulate):
     return nfma
 
 
-def gen_spmv_smem(em, fname, m, out_pad, accumulate):
+def gen_spmv_smem(em, fname, m, out_pad, accumulate, lockstep=False):
     """out (+)= M . x, x read from shared memory with 128-bit loads (column of length cols)."""
     rows, cols = m.shape
+    em.lockstep, em.nacc = lockstep, 0
     em.w("template <typename R, typename Src>")
     em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const Src& x) {{")
     em.w("  using P = typename Pk<R>::T;")
@@ -131,6 +140,7 @@ def gen_spmv_smem(em, fname, m, out_pad, accumulate):
 
 def gen_spmv_reg(em, fname, m, in_pad, out_pad, accumulate):
     """out (+)= M . x with x in registers."""
+    em.lockstep = False
     em.w("template <typename R>")
     em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const typename Pk<R>::T (&x)[{in_pad}]) {{")
     touched = None if accumulate else set()
@@ -152,6 +162,7 @@ def gen_spmv_reg(em, fname, m, in_pad, out_pad, accumulate):
 def gen_spmv_chunks(em, fname, m, in_pad, out_pad):
     """out += M . x where x arrives in chunks of 4 entries from a kernel-supplied source
     (js.template chunk<c>(x4) yields x[4c .. 4c+3]): the full x column never sits in registers."""
+    em.lockstep, em.nacc = True, 0
     em.w("template <typename R, typename JS>")
     em.w(f"__device__ __forceinline__ void {fname}(typename Pk<R>::T (&out)[{out_pad}], const JS& js) {{")
     nfma = 0
@@ -211,16 +222,35 @@ def generate(order):
     stats["volume"] = gen_star_sweep(em, "volume", [kdm[i] for i in range(3)], B, B, pad4(B), True)
     # --- face operators
     for f in range(4):
-        stats[f"fMrT_{f}"] = gen_spmv_smem(em, f"fMrT_{f}", z["fMrT"][f], pad4(B2), False)
+        stats[f"fMrT_{f}"] = gen_spmv_smem(em, f"fMrT_{f}", z["fMrT"][f], pad4(B2), False, lockstep=True)
         stats[f"rT_{f}"] = gen_spmv_smem(em, f"rT_{f}", z["rT"][f], pad4(B2), False)
         stats[f"rDivM_{f}"] = gen_spmv_chunks(em, f"rDivM_{f}", z["rDivM"][f], pad4(B2), pad4(B))
     for h in range(3):
         stats[f"fP_{h}"] = gen_spmv_reg(em, f"fP_{h}", z["fP"][h], pad4(B2), pad4(B2), False)
+    # --- face-projection path (kernels_faceproj.cuh): the local kernel stores F_f = fMrT_f . I = D . (rT_f . I) per face
+    #     (the face mass matrix D is diagonal and the same for every face), the neighbor kernel applies
+    #     fPD_h = fP_h . D^-1 and rDivM_i with its input in registers.
+    dvec = np.zeros(B2)
+    for f in range(4):
+        rt, fm = z["rT"][f], z["fMrT"][f]
+        assert np.array_equal(rt != 0, fm != 0)
+        for k in range(B2):
+            nzc = np.nonzero(rt[k])[0]
+            ratio = fm[k, nzc] / rt[k, nzc]
+            assert np.allclose(ratio, ratio[0], rtol=1e-12, atol=0), "fMrT is not a row scaling of rT"
+            assert dvec[k] == 0 or np.isclose(dvec[k], ratio[0], rtol=1e-12), "face mass matrix differs between faces"
+            dvec[k] = ratio[0]
+    for h in range(3):
+        stats[f"fPD_{h}"] = gen_spmv_reg(em, f"fPD_{h}", z["fP"][h] / dvec[None, :], pad4(B2), pad4(B2), False)
+    for f in range(4):
+        stats[f"rDivMr_{f}"] = gen_spmv_reg(em, f"rDivMr_{f}", z["rDivM"][f], pad4(B2), pad4(B), True)
     PT = "typename Pk<R>::T"
     gen_dispatch(em, "fMrT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src="Src")
     gen_dispatch(em, "rT", 4, f"{PT} (&out)[{pad4(B2)}], const Src& x", "out, x", src="Src")
     gen_dispatch(em, "rDivM", 4, f"{PT} (&out)[{pad4(B)}], const JS& js", "out, js", src="JS")
     gen_dispatch(em, "fP", 3, f"{PT} (&out)[{pad4(B2)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
+    gen_dispatch(em, "fPD", 3, f"{PT} (&out)[{pad4(B2)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
+    gen_dispatch(em, "rDivMr", 4, f"{PT} (&out)[{pad4(B)}], const {PT} (&x)[{pad4(B2)}]", "out, x")
     # --- ADER driver: the kernel supplies a context with src()/finish() (hand-written)
     em.w("template <typename R, typename Ctx>")
     em.w("__device__ __forceinline__ void ader_run(Ctx& c) {")

@@ -317,6 +317,69 @@ int ssb_ader_local(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t 
   return c->ksLocal->local(p, true, true, static_cast<cudaStream_t>(stream));
 }
 
+int ssb_local_faceproj(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t local_int, ssb_array_t face_proj,
+                       const uint8_t* face_types, long long n, const int* perm, void* stream) {
+  LocalParams p;
+  ssb_array_t none = {nullptr, nullptr, 0};
+  const int rc = fillLocal(c, p, dofs, idofs, none, local_int, face_types, nullptr, n, perm);
+  if (rc != 0) {
+    return rc;
+  }
+  p.faceProj = conv(face_proj);
+  if (n > 0 && !p.faceProj.present()) {
+    return SSB_EINVAL;
+  }
+  return c->ksLocal->local(p, false, true, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_ader_local_faceproj(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t derivs, ssb_array_t local_int,
+                            ssb_array_t face_proj, const uint8_t* face_types, const double* coeffs, long long n,
+                            const int* perm, void* stream) {
+  LocalParams p;
+  if (coeffs == nullptr) {
+    return SSB_EINVAL;
+  }
+  const int rc = fillLocal(c, p, dofs, idofs, derivs, local_int, face_types, coeffs, n, perm);
+  if (rc != 0) {
+    return rc;
+  }
+  p.faceProj = conv(face_proj);
+  if (n > 0 && !p.faceProj.present()) {
+    return SSB_EINVAL;
+  }
+  return c->ksLocal->local(p, true, true, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_neigh_faceproj(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
+                       ssb_array_t face_proj, ssb_array_t neigh_int, const uint8_t* face_types,
+                       const uint8_t* face_rel, long long n, const int* perm, void* stream) {
+  if (c == nullptr || n < 0 || face_rel == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  NeighParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  p.neighInt = conv(neigh_int);
+  p.faceProj = conv(face_proj);
+  p.nbPtrs = nb_ptrs;
+  p.nbIdx = nb_idx;
+  if (!p.dofs.present() || !p.neighInt.present() ||
+      (nb_ptrs == nullptr && (nb_idx == nullptr || !p.faceProj.present()))) {
+    return SSB_EINVAL;
+  }
+  p.useFaceProj = 1;
+  p.faceTypes = face_types;
+  p.faceRel = face_rel;
+  p.perm = perm;
+  p.n = n;
+  p.ldg = c->ldq;
+  // the face-projection kernel lives in the full-column translation units (both precisions)
+  return c->ks->neigh(p, static_cast<cudaStream_t>(stream));
+}
+
 int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* coeffs, long long n,
                void* stream) {
   if (c == nullptr || coeffs == nullptr || n < 0) {

@@ -5,6 +5,19 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Lock-step markers of the generated operator code (codegen/gen_ops.py emits SSB_LS(i) every 64 FMAs in the operators
+// that every thread of a CTA executes uniformly).  With SSB_LOCKSTEP = P > 0 every (P/64)-th marker is a CTA barrier:
+// the warps of a CTA cannot drift apart in a straight-line instruction stream that is larger than the instruction
+// caches, so they share every fetched line (tools/ubench/gen_ifetch4.py).
+#ifndef SSB_LOCKSTEP
+#define SSB_LOCKSTEP 0
+#endif
+#if SSB_LOCKSTEP > 0
+#define SSB_LS(i) do { if ((i) % (SSB_LOCKSTEP / 64) == 0) __syncthreads(); } while (0)
+#else
+#define SSB_LS(i) do { } while (0)
+#endif
+
 namespace ssb {
 
 // ---------------------------------------------------------------------------------------

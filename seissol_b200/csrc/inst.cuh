@@ -3,6 +3,7 @@
 // and includes gen/ops_o<SSB_ORDER>.cuh before this header.
 #include "api_internal.h"
 #include "kernels_elastic.cuh"
+#include "kernels_faceproj.cuh"
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
@@ -74,6 +75,15 @@ struct Gen {
   __device__ __forceinline__ static void fP(int h, typename Pk<R>::T (&out)[kB2P], const typename Pk<R>::T (&x)[kB2P]) {
     SSB_GEN::fP<R>(h, out, x);
   }
+  template <typename R>
+  __device__ __forceinline__ static void fPD(int h, R (&out)[kB2P], const R (&x)[kB2P]) {
+    static_assert(Pk<R>::V == 1, "the face-projection path is scalar");
+    SSB_GEN::fPD<R>(h, out, x);
+  }
+  template <typename R>
+  __device__ __forceinline__ static void rDivMr(int f, R (&out)[kBP], const R (&x)[kB2P]) {
+    SSB_GEN::rDivMr<R>(f, out, x);
+  }
 };
 
 using Real = SSB_REAL;
@@ -111,7 +121,45 @@ int localEntry(const LocalParams& p, bool ader, bool local, cudaStream_t stream)
   return launchLocal<false, true>(p, stream);
 }
 
+// elements per CTA of the face-projection neighbor kernel: two resident CTAs per SM (about 100 KB each)
+constexpr int neighFpElems() {
+  const int per = padOdd16(4 * kNQ * Gen::kB2P + 4 * 81, sizeof(Real)) * int(sizeof(Real));
+  const int e = 101000 / per;
+  return e > 28 ? 28 : e;
+}
+#ifdef SSB_E_NEIGHFP
+constexpr int ENF = SSB_E_NEIGHFP;
+#else
+constexpr int ENF = neighFpElems();
+#endif
+
+int neighFpEntry(const NeighParams& p, cudaStream_t stream) {
+#if SSB_PACK_F32 == 1
+  using P = NeighFpPlan<Real, Gen, ENF>;
+  auto kern = k_neigh_fp<Real, Gen, ENF>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
+    if (err != cudaSuccess) {
+      return int(err);
+    }
+    configured = true;
+  }
+  if (p.n <= 0) {
+    return 0;
+  }
+  const unsigned grid = gridFor((p.n + ENF - 1) / ENF);
+  kern<<<grid, P::threads, P::bytes + smemPad(), stream>>>(p);
+  return int(cudaGetLastError());
+#else
+  return -2;
+#endif
+}
+
 int neighEntry(const NeighParams& p, cudaStream_t stream) {
+  if (p.faceProj.present() || p.useFaceProj) {
+    return neighFpEntry(p, stream);
+  }
   using P = NeighPlan<Real, Gen, EN>;
   auto kern = k_neigh<Real, Gen, EN>;
   static bool configured = false;

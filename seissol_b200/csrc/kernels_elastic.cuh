@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_LOCAL) k_local(cons
 
   if constexpr (LOCAL) {
     const R* const Ie = RD;  // interleaved I
+    const bool wantProj = p.faceProj.present();
     // ---- volume: Q += sum_i kDivM_i . (I . star_i)
     G::template volume<R>(acc, Ie + r0 * BP * V, Ie + r1 * BP * V, Ie + r2 * BP * V, s);
 
@@ -409,7 +410,25 @@ __global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_LOCAL) k_local(cons
       if constexpr (sizeof(R) == 8) {
         loadA();
       }
+      if constexpr (V == 1) {
+        // face projections for the neighbor kernel (kernels_faceproj.cuh): F_f of an element is one contiguous
+        // [9][B2P] block of its face buffer and leaves by a bulk store.  The store of face f-1 has to be done reading
+        // its buffer before anybody passes the barrier below and overwrites it with F_{f+1}.
+        if (wantProj) {
+          fence_async_smem();
+          if (f >= 1 && tid < E) {
+            tma_store_wait_read();
+          }
+        }
+      }
       __syncthreads();
+      if constexpr (V == 1) {
+        if (wantProj && tid < E && myElem >= 0) {
+          tma_store(static_cast<R*>(const_cast<void*>(p.faceProj.at(myElem))) + f * kNQ * B2P,
+                    myRQ + (f & 1) * kNQ * B2P, kNQ * B2P * sizeof(R));
+          tma_store_commit();
+        }
+      }
       G::template rDivM<R>(f, acc, JChunks<R, B2P>{Fe, a});
     }
 

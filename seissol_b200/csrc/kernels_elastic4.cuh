@@ -277,6 +277,7 @@ __device__ __forceinline__ void localBody4(const LocalParams& p, unsigned char* 
 
     if constexpr (LOCAL) {
       const R* const Ie = RD;  // interleaved I
+      const bool wantProj = p.faceProj.present();
       G::template volume<R, H>(acc, Ie + r0 * BP * V, Ie + r1 * BP * V, Ie + r2 * BP * V, s);
 
       if (ADER) {
@@ -308,7 +309,23 @@ __device__ __forceinline__ void localBody4(const LocalParams& p, unsigned char* 
             }
           }
         }
+        if constexpr (V == 1) {
+          // face projections for the neighbor kernel (kernels_faceproj.cuh), see k_local
+          if (wantProj) {
+            fence_async_smem();
+            if (f >= 1 && H == 0 && tid < E) {
+              tma_store_wait_read();
+            }
+          }
+        }
         __syncthreads();
+        if constexpr (V == 1) {
+          if (wantProj && H == 0 && tid < E && myElem >= 0) {
+            tma_store(static_cast<R*>(const_cast<void*>(p.faceProj.at(myElem))) + f * kNQ * B2P,
+                      myRQ + (f & 1) * kNQ * B2P, kNQ * B2P * sizeof(R));
+            tma_store_commit();
+          }
+        }
         G::template rDivM<R, H>(f, acc, JChunks<R, B2P>{Fe, a});
       }
 

@@ -1,0 +1,207 @@
+// Neighbor flux from FACE PROJECTIONS (generation 5 of the neighbor kernel).
+//
+// Reference: Neighbor::computeBatchedNeighborsIntegral (src/Kernels/LinearCK/Neighbor.cpp:111-188),
+//   Q_i += rDivM_i . fP_h . rT_j . I_nb . AminusT_i      (kernel::neighboringFlux(h,j,i), codegen/kernels/aderdg.py:414-461)
+//
+// The face mass matrix is diagonal and identical on the four faces, fMrT_f = D . rT_f (checked by the generator), so the
+// LOCAL kernel already holds F_f = fMrT_f . I = D . (rT_f . I) for every face f of its element while it evaluates the
+// local flux.  It stores these four [9][B2P] blocks (`face_proj`, 4 x 864 B at order 6 / float) next to I, and this
+// kernel gathers the block of face j of each neighbor instead of the neighbor's whole I:
+//   Q_i += rDivM_i . (fP_h D^-1) . (F_j,nb . AminusT_i)
+// * 4 x 864 B gathered per element instead of 4 x 2016 B,
+// * the 16 rT_j bodies (7.5 k instructions = 119 KB of a 206 KB kernel) and 39 % of the FMAs are gone,
+// * the 9x9 flux-solver product is applied FIRST (it commutes with the left operators), so a thread keeps its column
+//   in registers from the tile to the accumulator: no shared-memory exchange and no barrier between the stages.
+// Rounding differs from the reference's evaluation order by a few ulp (tests hold the kernel to 2e-6 / 5e-15 against the
+// oracle's reference order).
+#pragma once
+#include "common.cuh"
+#include "params.cuh"
+#include "kernels_elastic.cuh"
+
+namespace ssb {
+
+template <typename R, typename G, int E>
+struct NeighFpPlan {
+  static constexpr int BP = G::kBP;
+  static constexpr int B2P = G::kB2P;
+  static constexpr int TEN = kNQ * BP;   // one element tensor
+  static constexpr int PRJ = kNQ * B2P;  // one face projection
+  static constexpr int AM = 4 * 81;      // nAmNm1[4][81]
+  static_assert(3 * PRJ >= TEN, "the own Q tile re-uses the space of the projections of faces 0..2");
+  // per element: projections of faces 0..3 | nAmNm1; stride padded to an odd multiple of 16 bytes
+  static constexpr int SE = padOdd16(4 * PRJ + AM, sizeof(R));
+  static constexpr int offA = 4 * PRJ;
+  static constexpr size_t barOffset = (size_t(E) * SE * sizeof(R) + 15) / 16 * 16;
+  static constexpr size_t bytes = barOffset + 16;
+  static constexpr int threads = (kNQ * E + 31) / 32 * 32;
+};
+
+#ifndef SSB_MINB_NEIGHFP
+#define SSB_MINB_NEIGHFP 2
+#endif
+template <typename R, typename G, int E>
+__global__ void __launch_bounds__((NeighFpPlan<R, G, E>::threads), SSB_MINB_NEIGHFP) k_neigh_fp(const NeighParams p) {
+  using P = NeighFpPlan<R, G, E>;
+  constexpr int BP = P::BP, B2P = P::B2P, TEN = P::TEN, PRJ = P::PRJ;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  R* const smem = reinterpret_cast<R*>(smemRaw);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::barOffset);  // bar[0]: projections + nAmNm1, bar[1]: own Q
+
+  const int tid = threadIdx.x;
+  const bool active = tid < kNQ * E;
+  const int g = active ? tid % E : 0;
+  const int q = active ? tid / E : 0;
+  if (tid == 0) {
+    mbar_init(bar, E);
+    mbar_init(bar + 1, E);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long nBatches = (p.n + E - 1) / E;
+  uint32_t phase = 0;
+  for (long long batch = blockIdx.x; batch < nBatches; batch += gridDim.x) {
+    const long long slot = batch * E;
+
+    // ---- loader threads: element slot+tid.  One bulk copy per regular face (block j of the neighbor's projections)
+    //      and one for nAmNm1.
+    long long myElem = -1;
+    R* const myTile = smem + (tid < E ? tid : 0) * P::SE;
+    if (tid < E) {
+      const long long sl = slot + tid;
+      if (sl < p.n) {
+        myElem = p.perm != nullptr ? p.perm[sl] : sl;
+      }
+      if (myElem >= 0) {
+        uchar4 t = make_uchar4(0, 0, 0, 0);
+        if (p.faceTypes != nullptr) {
+          t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * myElem);
+        }
+        const uint8_t ftl[4] = {t.x, t.y, t.z, t.w};
+        const uint2 rr = *reinterpret_cast<const uint2*>(p.faceRel + 8 * myElem);
+        const int fjl[4] = {int(rr.x & 0xff), int((rr.x >> 16) & 0xff), int(rr.y & 0xff), int((rr.y >> 16) & 0xff)};
+        const R* src[4];
+        uint32_t bytes = P::AM * sizeof(R);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          src[f] = nullptr;
+          if (ftl[f] == 0) {
+            const R* base = p.nbPtrs != nullptr ? static_cast<const R*>(p.nbPtrs[4 * myElem + f])
+                                                : static_cast<const R*>(p.faceProj.at(p.nbIdx[4 * myElem + f]));
+            if (base != nullptr) {
+              src[f] = base + fjl[f] * PRJ;
+              bytes += PRJ * sizeof(R);
+            }
+          }
+        }
+        mbar_arrive_expect_tx(bar, bytes);
+        tma_load(myTile + P::offA, p.neighInt.at(myElem), P::AM * sizeof(R), bar);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          if (src[f] != nullptr) {
+            tma_load(myTile + f * PRJ, src[f], PRJ * sizeof(R), bar);
+          }
+        }
+      } else {
+        mbar_arrive_expect_tx(bar, 0);
+      }
+    }
+
+    // ---- per-thread face metadata of element g
+    const long long sl = slot + g;
+    const long long el = sl < p.n ? (p.perm != nullptr ? p.perm[sl] : sl) : -1;
+    bool keep[4] = {false, false, false, false};
+    int fh[4] = {0, 0, 0, 0};
+    if (el >= 0) {
+      uchar4 t = make_uchar4(0, 0, 0, 0);
+      if (p.faceTypes != nullptr) {
+        t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
+      }
+      const uint2 rr = *reinterpret_cast<const uint2*>(p.faceRel + 8 * el);
+      fh[0] = (rr.x >> 8) & 0xff; fh[1] = (rr.x >> 24) & 0xff; fh[2] = (rr.y >> 8) & 0xff; fh[3] = (rr.y >> 24) & 0xff;
+      keep[0] = t.x == 0; keep[1] = t.y == 0; keep[2] = t.z == 0; keep[3] = t.w == 0;
+      if (p.nbPtrs != nullptr) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          keep[f] = keep[f] && p.nbPtrs[4 * el + f] != nullptr;
+        }
+      }
+    }
+
+    R acc[BP];
+#pragma unroll
+    for (int k = 0; k < BP; ++k) {
+      acc[k] = R(0);
+    }
+    const R* const tile = smem + g * P::SE;
+
+    mbar_wait(bar, phase);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      // x = column q of (F_nb . AminusT_f)
+      R x[B2P];
+#pragma unroll
+      for (int k = 0; k < B2P; ++k) {
+        x[k] = R(0);
+      }
+      const R* const A = tile + P::offA + 81 * f + 9 * q;
+      const R* const Fnb = tile + f * PRJ;
+#pragma unroll
+      for (int c = 0; c < kNQ; ++c) {
+        const R a = A[c];
+#pragma unroll
+        for (int k4 = 0; k4 < B2P / 4; ++k4) {
+          R t[4];
+          ld4(t, Fnb + c * B2P + 4 * k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[4 * k4 + i] = fma(a, t[i], x[4 * k4 + i]);
+          }
+        }
+      }
+      // faces without a regular neighbor loaded no tile: x came from stale shared memory -> exact zero (select)
+#pragma unroll
+      for (int k = 0; k < B2P; ++k) {
+        x[k] = keep[f] ? x[k] : R(0);
+      }
+      R F[B2P];
+      G::template fPD<R>(fh[f], F, x);
+      if (f == 3) {
+        // everybody is done with the tiles of faces 0..2: the own Q tensor lands there while face 3 is computed
+        __syncthreads();
+        if (tid < E) {
+          if (myElem >= 0) {
+            mbar_arrive_expect_tx(bar + 1, TEN * sizeof(R));
+            tmaLoadTensor<R, BP>(myTile, static_cast<const R*>(p.dofs.at(myElem)), p.ldg, bar + 1);
+          } else {
+            mbar_arrive_expect_tx(bar + 1, 0);
+          }
+        }
+      }
+      G::template rDivMr<R>(f, acc, F);
+    }
+
+    // ---- Q += acc
+    mbar_wait(bar + 1, phase);
+    phase ^= 1;
+    if (active && el >= 0) {
+      R* const col = const_cast<R*>(tile) + q * BP;
+#pragma unroll
+      for (int k4 = 0; k4 < BP / 4; ++k4) {
+        R t[4];
+        ld4(t, col + 4 * k4);
+        st4(col + 4 * k4, t[0] + acc[4 * k4], t[1] + acc[4 * k4 + 1], t[2] + acc[4 * k4 + 2], t[3] + acc[4 * k4 + 3]);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid < E && myElem >= 0) {
+      tmaStoreTensor<R, BP>(static_cast<R*>(const_cast<void*>(p.dofs.at(myElem))), myTile, p.ldg);
+      tma_store_wait_read();
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace ssb

@@ -13,6 +13,7 @@ struct LocalParams {
   ElemArray idofs;     // I: out if ader, in if !ader       (LTS::Buffers / Idofs scratch)
   ElemArray derivs;    // optional derivative family, out   (LTS::Derivatives)
   ElemArray localInt;  // LocalIntegrationData: star[3][24], nApNm1[4][81]
+  ElemArray faceProj;  // optional out: F_f = fMrT_f . I, [4][9][B2P] per element (kernels_faceproj.cuh)
   const uint8_t* faceTypes;  // [n][4] FaceType, may be null (= all regular)
   const int* perm;           // optional processing order
   long long n;
@@ -28,11 +29,13 @@ struct NeighParams {
   const void* const* nbPtrs;  // [n][4] pointers to the neighbors' I (LTS::FaceNeighbors) or null
   const long long* nbIdx;     // else [n][4] indices into idofs
   ElemArray idofs;
+  ElemArray faceProj;         // face-projection path: nbIdx indexes this array; nbPtrs point to the neighbors' blocks
   const uint8_t* faceTypes;   // [n][4] or null
   const uint8_t* faceRel;     // [n][4][2] = {neighbor's face j, orientation h}
   const int* perm;
   long long n;
   int ldg;
+  int useFaceProj;            // nbPtrs / nbIdx refer to face projections (ssb_neigh_faceproj)
 };
 
 struct TaylorParams {

@@ -8,6 +8,7 @@ src/Proxy/KernelHost.h:29-56), same timing protocol (one untimed warm-up pass, t
 described in DESIGN.md §2; all arithmetic happens in libseissol_b200.so.
 """
 import math
+import os
 import time
 
 import numpy as np
@@ -147,15 +148,23 @@ class ProxyData:
     def bytes_resident(self):
         return sum(x.numel() * x.element_size() for x in
                    (self.dofs, self.buffers, self.local_int, self.neigh_int, self.face_rel,
-                    self.face_types, self.neighbors))
+                    self.face_types, self.neighbors) + ((self.face_proj,) if getattr(self, "face_proj", None) is not None else ()))
 
 
 class ProxyKernels:
     """Kernel-name dispatch (getProxyKernelDevice, src/Proxy/KernelDevice.cpp:126-150)."""
 
-    def __init__(self, ctx, data):
+    def __init__(self, ctx, data, faceproj=None):
+        """faceproj: route `localwoader`/`local` + `neigh` through the face-projection path (ssb_local_faceproj +
+        ssb_neigh_faceproj: the local kernel stores F_f = fMrT_f I per face, the neighbor kernel gathers those blocks
+        instead of the neighbors' I).  Default: on (environment SSB_FACEPROJ=0 switches back to ssb_local + ssb_neigh)."""
         self.ctx, self.d = ctx, data
         self.coeffs = integrate_coeffs(ctx.order, 0.0, TIMESTEP)
+        if faceproj is None:
+            faceproj = os.environ.get("SSB_FACEPROJ", "1") != "0"
+        self.faceproj = bool(faceproj)
+        if self.faceproj and getattr(data, "face_proj", None) is None:
+            data.face_proj = data.torch.zeros((data.cells, ctx.face_proj_reals()), dtype=data.dtype, device=data.device)
 
     def ader(self, stream=None):
         d = self.d
@@ -164,6 +173,10 @@ class ProxyKernels:
 
     def localwoader(self, stream=None):
         d = self.d
+        if self.faceproj:
+            self.ctx.local_faceproj(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.local_int),
+                                    api.strided(d.face_proj), d.face_types, d.cells, stream=stream)
+            return
         self.ctx.local(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.local_int),
                        d.face_types, d.cells, stream=stream)
 
@@ -173,7 +186,10 @@ class ProxyKernels:
         bound; the two smaller kernels run 35 % faster although I makes a round trip through L2/HBM
         (profiles/)."""
         d = self.d
-        if fused:
+        if fused and self.faceproj:
+            self.ctx.ader_local_faceproj(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
+                                         api.strided(d.face_proj), d.face_types, self.coeffs, d.cells, stream=stream)
+        elif fused:
             self.ctx.ader_local(api.strided(d.dofs), api.strided(d.buffers), None, api.strided(d.local_int),
                                 d.face_types, self.coeffs, d.cells, stream=stream)
         else:
@@ -182,6 +198,10 @@ class ProxyKernels:
 
     def neigh(self, stream=None):
         d = self.d
+        if self.faceproj:
+            self.ctx.neigh_faceproj(api.strided(d.dofs), api.strided(d.face_proj), api.strided(d.neigh_int),
+                                    d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
+            return
         self.ctx.neigh(api.strided(d.dofs), api.strided(d.buffers), api.strided(d.neigh_int),
                        d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
 
@@ -338,7 +358,7 @@ class DrProxyKernels(ProxyKernels):
     """godunov_dr, neigh_dr, all_dr (src/Proxy/KernelHost.h:29-56)."""
 
     def __init__(self, ctx, data, dr):
-        super().__init__(ctx, data)
+        super().__init__(ctx, data, faceproj=False)   # all faces are DynamicRupture: no regular neighbor flux
         self.dr = dr
         self._plus = dr.der_array(dr.plus_cell)
         self._minus = dr.der_array(dr.minus_cell)

@@ -33,6 +33,26 @@ def gpu(built_library):
     return torch, api, proxy
 
 
+def face_proj_host(tab, I):
+    """F_f = fMrT_f . I for the four faces, logical layout [n, 4, B2, 9] (what ssb_local_faceproj stores)."""
+    return np.stack([np.matmul(tab["fMrT"][f], I) for f in range(4)], 1)
+
+
+def face_proj_to_device(torch, ctx, F, device):
+    n, _, b2, _ = F.shape
+    b2p = (b2 + 3) // 4 * 4
+    out = np.zeros((n, 4, 9, b2p), dtype=F.dtype)
+    out[:, :, :, :b2] = F.transpose(0, 1, 3, 2)
+    return torch.from_numpy(out.reshape(n, -1)).to(device)
+
+
+def face_proj_from_device(ctx, t):
+    b2 = ctx.order * (ctx.order + 1) // 2
+    b2p = (b2 + 3) // 4 * 4
+    x = t.cpu().numpy().reshape(t.shape[0], 4, 9, b2p)
+    return np.ascontiguousarray(x[:, :, :, :b2].transpose(0, 1, 3, 2)), x[:, :, :, b2:]
+
+
 def make(order, dt, n, api, proxy, seed=5, reference_layout=False):
     ctx = api.Context(order, np.dtype(dt).itemsize, reference_layout=reference_layout)
     host = O.proxy_data(order, n, dt, seed=seed)
@@ -67,7 +87,8 @@ def test_ader_with_derivatives(gpu, order, dt):
 
 
 @pytest.mark.parametrize("order,dt", CONFIGS)
-def test_localwoader_and_fused_local(gpu, order, dt):
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_localwoader_and_fused_local(gpu, order, dt, faceproj):
     torch, api, proxy = gpu
     n = 200
     ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=9)
@@ -77,25 +98,35 @@ def test_localwoader_and_fused_local(gpu, order, dt):
     star = O.star_dense(host["star"], tab["star_pattern"])
     I = O.ader(tab, host["Q"], star, c)
     want = O.local(tab, host["Q"], I, star, O.flux_dense(host["Aplus"]), host["face_types"])
-    # fused ader+local
-    k = proxy.ProxyKernels(ctx, data)
-    k.local()
-    torch.cuda.synchronize()
-    assert rel_l2(data.to_logical(data.buffers), I) < step_tol(dt)
-    assert rel_l2(data.to_logical(data.dofs), want) < step_tol(dt)
-    assert rel_l2(data.to_logical(data.dofs) - host["Q"], want - host["Q"]) < 50 * step_tol(dt)
+    # ader + local (two launches; `fused` = one launch)
+    for fused in (False, True):
+        data = proxy.ProxyData.from_host(ctx, host)
+        k = proxy.ProxyKernels(ctx, data, faceproj=faceproj)
+        k.local(fused=fused)
+        torch.cuda.synchronize()
+        assert rel_l2(data.to_logical(data.buffers), I) < step_tol(dt)
+        assert rel_l2(data.to_logical(data.dofs), want) < step_tol(dt)
+        assert rel_l2(data.to_logical(data.dofs) - host["Q"], want - host["Q"]) < 50 * step_tol(dt)
+        if faceproj:
+            # the by-product of the local flux: F_f = fMrT_f . I for ALL faces (DR faces included), padding rows zero
+            got, pad = face_proj_from_device(ctx, data.face_proj)
+            assert rel_l2(got, face_proj_host(tab, I)) < step_tol(dt)
+            assert np.all(pad == 0)
     # stand-alone localwoader on the oracle's I
     host2 = dict(host)
     host2["I"] = I
     data2 = proxy.ProxyData.from_host(ctx, host2)
-    proxy.ProxyKernels(ctx, data2).localwoader()
+    proxy.ProxyKernels(ctx, data2, faceproj=faceproj).localwoader()
     torch.cuda.synchronize()
     assert rel_l2(data2.to_logical(data2.dofs), want) < step_tol(dt)
 
 
 @pytest.mark.parametrize("order,dt", CONFIGS)
 @pytest.mark.parametrize("sort", [False, True])
-def test_neighbor(gpu, order, dt, sort):
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_neighbor(gpu, order, dt, sort, faceproj):
+    """faceproj: ssb_neigh_faceproj on the projections F_f = fMrT_f . I_nb (computed here with the oracle's tables)
+    must give what the reference's rDivM_i fP_h rT_j I_nb AminusT_i gives."""
     torch, api, proxy = gpu
     n = 301
     ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=13)
@@ -106,7 +137,9 @@ def test_neighbor(gpu, order, dt, sort):
     data = proxy.ProxyData.from_host(ctx, host)
     if sort:
         data.sort_by_face_relation()
-    proxy.ProxyKernels(ctx, data).neigh()
+    if faceproj:
+        data.face_proj = face_proj_to_device(torch, ctx, face_proj_host(tab, host["I"]), data.device)
+    proxy.ProxyKernels(ctx, data, faceproj=faceproj).neigh()
     torch.cuda.synchronize()
     want = O.neighbor(tab, host["Q"], host["I"], host["neighbors"], O.flux_dense(host["Aminus"]),
                       host["face_rel"], host["face_types"])
@@ -115,7 +148,8 @@ def test_neighbor(gpu, order, dt, sort):
 
 
 @pytest.mark.parametrize("order,dt", [(6, np.float32), (6, np.float64)])
-def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt):
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt, faceproj):
     """Faces without a regular neighbor load no tile: whatever the previous kernel left in shared memory (here: NaN
     patterns pushed through torch scan/sort kernels) must not leak into the update (regression: NaN * 0)."""
     torch, api, proxy = gpu
@@ -132,7 +166,9 @@ def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt):
         poison.cumsum(0)
         torch.sort(poison)
         torch.sort(torch.full((1 << 22,), -1, device=data.device, dtype=torch.int32))    # 0xffffffff = NaN pattern
-    proxy.ProxyKernels(ctx, data).neigh()
+    if faceproj:
+        data.face_proj = face_proj_to_device(torch, ctx, face_proj_host(tab, host["I"]), data.device)
+    proxy.ProxyKernels(ctx, data, faceproj=faceproj).neigh()
     torch.cuda.synchronize()
     got = data.to_logical(data.dofs)
     assert np.isfinite(got).all()
@@ -142,14 +178,16 @@ def test_neighbor_boundary_faces_ignore_stale_shared_memory(gpu, order, dt):
 
 
 @pytest.mark.parametrize("order,dt,steps", [(6, np.float32, 10), (6, np.float64, 10), (4, np.float32, 10),
-                                            (6, np.float32, 50), (6, np.float64, 50)])
-def test_all_n_steps(gpu, order, dt, steps):
-    """BASELINE.json parity bar: DOFs after N = 10 and N = 50 steps of `all` within 1e-5 (f32) / 1e-11 (f64)."""
+                                            (5, np.float32, 10), (6, np.float32, 50), (6, np.float64, 50)])
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_all_n_steps(gpu, order, dt, steps, faceproj):
+    """BASELINE.json parity bar: DOFs after N = 10 and N = 50 steps of `all` within 1e-5 (f32) / 1e-11 (f64), on
+    >= 10 k elements for N = 10, through both neighbor paths."""
     torch, api, proxy = gpu
-    n = 2000 if steps == 10 else 600
+    n = 10007 if steps == 10 else 600
     ctx, host, data, tab, c = make(order, dt, n, api, proxy, seed=21)
     data.sort_by_face_relation()
-    k = proxy.ProxyKernels(ctx, data)
+    k = proxy.ProxyKernels(ctx, data, faceproj=faceproj)
     for _ in range(steps):
         k.all()
         host = O.proxy_step(tab, host, c, "all")

@@ -52,6 +52,30 @@ qbf64)
 part)
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $out/bench_part2.json 2> $out/bench_part2.err
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-overlap > $out/bench_part2_noov.json 2> $out/bench_part2_noov.err ;;
+ls)
+  timeout 600 tools/ubench/ifetch4 > $out/ifetch4.txt 2>&1
+  timeout 300 python tools/quick_bench.py > $out/qb_base.txt 2>&1
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py > $out/qb_$v.txt 2>&1
+  done
+  for v in $LSTEST; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_$v.log 2>&1; echo "exit $?" >> $out/pytest_$v.log
+  done ;;
+fp)
+  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_parity.log 2>&1; echo "exit $?" >> $out/pytest_parity.log
+  timeout 300 python tools/quick_bench.py > $out/qb_base.txt 2>&1
+  SSB_FACEPROJ=0 timeout 300 python tools/quick_bench.py > $out/qb_nofp.txt 2>&1
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py > $out/qb_$v.txt 2>&1
+  done ;;
+tma)
+  timeout 300 tools/ubench/tma_rate > $out/tma_rate.txt 2>&1 ;;
+ncufp)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 6 -c 3 -f -o $out/full_fp \
+      python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_full_fp.log 2>&1 ;;
 ubench)
   timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
 qb)
