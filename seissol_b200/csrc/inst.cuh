@@ -4,6 +4,7 @@
 #include "api_internal.h"
 #include "kernels_elastic.cuh"
 #include "kernels_faceproj.cuh"
+#include "kernels_elastic5.cuh"
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
@@ -40,6 +41,24 @@ inline size_t smemPad() {
     pad = e != nullptr ? std::atol(e) : 0;
   }
   return static_cast<size_t>(pad);
+}
+
+// SM count of the CURRENT device (cached per device ordinal)
+inline int smCount() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+  }
+  if (cache[dev] == 0) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = sms;
+  }
+  return cache[dev];
 }
 
 // Traits binding the generated operator code of one order to the kernel templates.
@@ -91,6 +110,49 @@ constexpr int EL = SSB_E_LOCAL;  // groups of V elements per CTA
 constexpr int EN = SSB_E_NEIGH;
 constexpr int VL = Pk<Real>::V;
 
+// Kernel generation of the split predictor / local kernels: generation 5 = persistent software-pipelined CTAs
+// (kernels_elastic5.cuh), generation 3 = one batch per CTA.  SSB_KGEN5 is a bit mask: 1 = local on generation 5,
+// 2 = predictor on generation 5.  Default (measured, profiles/r2_gen5_quick_bench.txt): single precision runs the local
+// kernel on generation 5 (3.65 vs 4.13 ms with face projections) and the predictor on generation 3 (1.83 vs 2.03 ms:
+// with all 16 warps of an SM issuing at once the instruction fetch of the straight-line stream thrashes more than the
+// pipelining gains); double precision stays on generations 3/4 (generation 5 spills there).
+inline int gen5Mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SSB_KGEN5");
+    v = e != nullptr ? std::atoi(e) : (sizeof(Real) == 4 ? 1 : 0);
+  }
+  return VL == 1 ? v : 0;
+}
+
+#if SSB_PACK_F32 == 1
+template <bool ADER>
+int launchLocal5(const LocalParams& p, cudaStream_t stream) {
+  using P = LocalPlan<Real, Gen, EL>;
+  auto kern = ADER ? k_ader5<Real, Gen, EL> : k_local5<Real, Gen, EL>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
+    if (err != cudaSuccess) {
+      return int(err);
+    }
+    if (dev >= 0 && dev < 64) {
+      configured[dev] = true;
+    }
+  }
+  if (p.n <= 0) {
+    return 0;
+  }
+  const long long batches = (p.n + EL - 1) / EL;
+  const long long resident = static_cast<long long>(SSB_MINB_LOCAL5) * smCount();
+  const unsigned grid = static_cast<unsigned>(batches < resident ? batches : resident);
+  kern<<<grid, blockThreads(EL), P::bytes + smemPad(), stream>>>(p);
+  return int(cudaGetLastError());
+}
+#endif
+
 template <bool ADER, bool LOCAL>
 int launchLocal(const LocalParams& p, cudaStream_t stream) {
   using P = LocalPlan<Real, Gen, EL>;
@@ -115,6 +177,14 @@ int localEntry(const LocalParams& p, bool ader, bool local, cudaStream_t stream)
   if (ader && local) {
     return launchLocal<true, true>(p, stream);
   }
+#if SSB_PACK_F32 == 1
+  if (ader && (gen5Mask() & 2)) {
+    return launchLocal5<true>(p, stream);
+  }
+  if (!ader && (gen5Mask() & 1)) {
+    return launchLocal5<false>(p, stream);
+  }
+#endif
   if (ader) {
     return launchLocal<true, false>(p, stream);
   }
@@ -133,8 +203,62 @@ constexpr int ENF = SSB_E_NEIGHFP;
 constexpr int ENF = neighFpElems();
 #endif
 
+// elements per CTA of the pipelined face-projection neighbor kernel (k_neigh_fp2): two resident CTAs per SM
+constexpr int neighFp2Elems() {
+  const int b2p = Gen::kB2P, prj = kNQ * b2p, ten = kNQ * Gen::kBP;
+  const int tail = ten > 2 * prj ? pad4i(ten - 2 * prj) : 0;
+  const int per = padOdd16(4 * prj + tail, sizeof(Real)) * int(sizeof(Real));
+  const int e = 107000 / per;
+  return e > 28 ? 28 : e;
+}
+#ifdef SSB_E_NEIGHFP2
+constexpr int ENF2 = SSB_E_NEIGHFP2;
+#else
+constexpr int ENF2 = neighFp2Elems();
+#endif
+
+// 1 = one batch per CTA (k_neigh_fp, default), 2 = persistent pipelined CTAs (k_neigh_fp2; SSB_NEIGHFP=2)
+inline int neighFpGeneration() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SSB_NEIGHFP");
+    v = (e != nullptr && e[0] == '2') ? 2 : 1;   // measured equal (2.63 vs 2.68 ms at 1 M elements): the simpler kernel is the default
+  }
+  return v;
+}
+
+#if SSB_PACK_F32 == 1
+int neighFp2Entry(const NeighParams& p, cudaStream_t stream) {
+  using P = NeighFp2Plan<Real, Gen, ENF2>;
+  auto kern = k_neigh_fp2<Real, Gen, ENF2>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
+    if (err != cudaSuccess) {
+      return int(err);
+    }
+    if (dev >= 0 && dev < 64) {
+      configured[dev] = true;
+    }
+  }
+  if (p.n <= 0) {
+    return 0;
+  }
+  const long long batches = (p.n + ENF2 - 1) / ENF2;
+  const long long resident = static_cast<long long>(SSB_MINB_NEIGHFP2) * smCount();
+  const unsigned grid = static_cast<unsigned>(batches < resident ? batches : resident);
+  kern<<<grid, P::threads, P::bytes + smemPad(), stream>>>(p);
+  return int(cudaGetLastError());
+}
+#endif
+
 int neighFpEntry(const NeighParams& p, cudaStream_t stream) {
 #if SSB_PACK_F32 == 1
+  if (neighFpGeneration() == 2) {
+    return neighFp2Entry(p, stream);
+  }
   using P = NeighFpPlan<Real, Gen, ENF>;
   auto kern = k_neigh_fp<Real, Gen, ENF>;
   static bool configured = false;

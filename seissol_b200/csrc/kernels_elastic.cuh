@@ -86,8 +86,10 @@ struct AderCtx {
       // derivative family (LTS / dynamic rupture consumers): straight to global memory
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        if (el[v] >= 0) {
-          R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(el[v]))) + p.derOffset[d] + q * p.derLd[d];
+        // a NULL entry in the derivative table: this element keeps no derivatives (Time.cpp:150-160)
+        R* const dbase = el[v] >= 0 ? static_cast<R*>(const_cast<void*>(p.derivs.at(el[v]))) : nullptr;
+        if (dbase != nullptr) {
+          R* dst = dbase + p.derOffset[d] + q * p.derLd[d];
 #pragma unroll
           for (int k4 = 0; k4 < N / 4; ++k4) {
             st4lane(dst + 4 * k4, v, out[4 * k4], out[4 * k4 + 1], out[4 * k4 + 2], out[4 * k4 + 3]);
@@ -267,12 +269,15 @@ __global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_LOCAL) k_local(cons
     const bool wantDer = p.derivs.present();
     // dQ(0) = Q copy into the derivative family (Time.cpp:109-116), from the staged tensor
     if (wantDer && tid < E && myElem >= 0) {
-      R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem))) + p.derOffset[0];
-      for (int c = 0; c < kNQ; ++c) {
-        tma_store(dst + c * p.derLd[0], myRQ + c * BP, BP * sizeof(R));
+      R* const dbase = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem)));
+      if (dbase != nullptr) {
+        R* dst = dbase + p.derOffset[0];
+        for (int c = 0; c < kNQ; ++c) {
+          tma_store(dst + c * p.derLd[0], myRQ + c * BP, BP * sizeof(R));
+        }
+        tma_store_commit();
+        tma_store_wait_read();
       }
-      tma_store_commit();
-      tma_store_wait_read();
     }
     PT icol[P::LD1];
     {

@@ -55,8 +55,9 @@ struct AderCtx4 {
     if (wantDer && active) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        if (el[v] >= 0) {
-          R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(el[v]))) + p.derOffset[d] + q * p.derLd[d];
+        R* const dbase = el[v] >= 0 ? static_cast<R*>(const_cast<void*>(p.derivs.at(el[v]))) : nullptr;
+        if (dbase != nullptr) {  // NULL table entry: no derivatives kept for this element
+          R* dst = dbase + p.derOffset[d] + q * p.derLd[d];
 #pragma unroll
           for (int pc = 0; pc < N / 4; ++pc) {
             st2lane(dst + 4 * pc + 2 * h, v, out[2 * pc], out[2 * pc + 1]);
@@ -171,12 +172,15 @@ __device__ __forceinline__ void localBody4(const LocalParams& p, unsigned char* 
       const bool wantDer = p.derivs.present();
       if (H == 0 && wantDer && tid < E && myElem >= 0) {
         // dQ(0) = Q copy into the derivative family (Time.cpp:109-116), from the staged tensor
-        R* dst = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem))) + p.derOffset[0];
-        for (int c = 0; c < kNQ; ++c) {
-          tma_store(dst + c * p.derLd[0], myRQ + c * BP, BP * sizeof(R));
+        R* const dbase = static_cast<R*>(const_cast<void*>(p.derivs.at(myElem)));
+        if (dbase != nullptr) {
+          R* dst = dbase + p.derOffset[0];
+          for (int c = 0; c < kNQ; ++c) {
+            tma_store(dst + c * p.derLd[0], myRQ + c * BP, BP * sizeof(R));
+          }
+          tma_store_commit();
+          tma_store_wait_read();
         }
-        tma_store_commit();
-        tma_store_wait_read();
       }
       PT icol[P::LD1 / 2];
       {

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "params.cuh"
 #include "kernels_elastic.cuh"
+#include "kernels_elastic5.cuh"
 
 namespace ssb {
 
@@ -201,6 +202,256 @@ __global__ void __launch_bounds__((NeighFpPlan<R, G, E>::threads), SSB_MINB_NEIG
       tma_store_wait_read();
     }
     __syncthreads();
+  }
+}
+
+// =======================================================================================================================
+// k_neigh_fp2: the same product as k_neigh_fp on PERSISTENT, SOFTWARE-PIPELINED CTAs.
+//
+// ncu on k_neigh_fp (profiles/r2_ncu_fp_summary.txt): 40 % of the warp samples sit in the mbarrier wait behind the
+// gather (perm -> face metadata -> neighbor index -> bulk copy: three dependent DRAM round trips), long_scoreboard
+// 3.45 stall cycles per issue, DRAM at 41 % -- the kernel is latency-bound, not bandwidth- or issue-bound.  Here
+//  * a CTA stays resident and walks its batches; the four face slots of an element form a ring: the tiles of faces
+//    0/1 of batch b+1 are requested as soon as every thread is done with them in batch b (barrier S1), the tiles of
+//    faces 2/3 of batch b at the top of batch b (they are needed only after faces 0 and 1 are computed);
+//  * the face metadata of batch b+1 is fetched at the top of batch b and the element ids (perm) two batches ahead,
+//    so that no dependent load chain is on the critical path;
+//  * the 9x9 flux-solver columns go straight from global memory to registers one face ahead (they need no staging: a
+//    thread reads 36 contiguous bytes of its own element) -> 3.4 KB of shared memory per element instead of 4.75 KB:
+//    28 elements per CTA, 16 warps per SM;
+//  * the update leaves as a bulk reduce-add into Q (kernels_elastic5.cuh): Q is never loaded; the update is staged in
+//    the slots of faces 2/3 (+ a small tail), which are dead after barrier S3.
+template <typename R, typename G, int E>
+struct NeighFp2Plan {
+  static constexpr int BP = G::kBP;
+  static constexpr int B2P = G::kB2P;
+  static constexpr int TEN = kNQ * BP;
+  static constexpr int PRJ = kNQ * B2P;
+  static constexpr int TAIL = TEN > 2 * PRJ ? pad4i(TEN - 2 * PRJ) : 0;
+  static constexpr int SE = padOdd16(4 * PRJ + TAIL, sizeof(R));
+  static constexpr int offStage = 2 * PRJ;
+  static constexpr size_t barOffset = (size_t(E) * SE * sizeof(R) + 15) / 16 * 16;
+  static constexpr size_t bytes = barOffset + 32;
+  static constexpr int threads = (kNQ * E + 31) / 32 * 32;
+};
+
+#ifndef SSB_MINB_NEIGHFP2
+#define SSB_MINB_NEIGHFP2 2
+#endif
+template <typename R, typename G, int E>
+__global__ void __launch_bounds__((NeighFp2Plan<R, G, E>::threads), SSB_MINB_NEIGHFP2) k_neigh_fp2(const NeighParams p) {
+  using P = NeighFp2Plan<R, G, E>;
+  using LM = LoaderMap<E, P::threads>;
+  constexpr int BP = P::BP, B2P = P::B2P, PRJ = P::PRJ;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  R* const smem = reinterpret_cast<R*>(smemRaw);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + P::barOffset);  // [0]: slot 0, [1]: slot 1, [2]: slots 2+3
+
+  const int tid = threadIdx.x;
+  const bool active = tid < kNQ * E;
+  const int g = active ? tid % E : 0;
+  const int q = active ? tid / E : 0;
+  const int le = LM::elem(tid);
+  R* const myTile = smem + (le >= 0 ? le : 0) * P::SE;
+  const R* const tile = smem + g * P::SE;
+  if (tid == 0) {
+    mbar_init(bar, E);
+    mbar_init(bar + 1, E);
+    mbar_init(bar + 2, E);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long nBatches = (p.n + E - 1) / E;
+  const long long stride = gridDim.x;
+  auto slotElem = [&](long long batch, int e) -> long long {
+    const long long sl = batch * E + e;
+    return (batch < nBatches && sl < p.n) ? (p.perm != nullptr ? p.perm[sl] : sl) : -1;
+  };
+  // compute-thread metadata: bits 2f..2f+1 = orientation h of face f, bit 8+f = face f has a regular neighbor
+  auto faceMeta = [&](long long elem) -> unsigned {
+    if (elem < 0) {
+      return 0u;
+    }
+    uchar4 t = make_uchar4(0, 0, 0, 0);
+    if (p.faceTypes != nullptr) {
+      t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * elem);
+    }
+    const uint2 rr = *reinterpret_cast<const uint2*>(p.faceRel + 8 * elem);
+    unsigned m = ((rr.x >> 8) & 3u) | (((rr.x >> 24) & 3u) << 2) | (((rr.y >> 8) & 3u) << 4) | (((rr.y >> 24) & 3u) << 6);
+    bool k0 = t.x == 0, k1 = t.y == 0, k2 = t.z == 0, k3 = t.w == 0;
+    if (p.nbPtrs != nullptr) {
+      k0 = k0 && p.nbPtrs[4 * elem + 0] != nullptr; k1 = k1 && p.nbPtrs[4 * elem + 1] != nullptr;
+      k2 = k2 && p.nbPtrs[4 * elem + 2] != nullptr; k3 = k3 && p.nbPtrs[4 * elem + 3] != nullptr;
+    }
+    return m | (k0 ? 0x100u : 0u) | (k1 ? 0x200u : 0u) | (k2 ? 0x400u : 0u) | (k3 ? 0x800u : 0u);
+  };
+  // loader metadata: the four projection blocks this element gathers (nullptr: nothing to load)
+  auto faceSrc = [&](long long elem, const R* (&src)[4]) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      src[f] = nullptr;
+    }
+    if (elem < 0) {
+      return;
+    }
+    uchar4 t = make_uchar4(0, 0, 0, 0);
+    if (p.faceTypes != nullptr) {
+      t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * elem);
+    }
+    const uint8_t ftl[4] = {t.x, t.y, t.z, t.w};
+    const uint2 rr = *reinterpret_cast<const uint2*>(p.faceRel + 8 * elem);
+    const int fjl[4] = {int(rr.x & 0xff), int((rr.x >> 16) & 0xff), int(rr.y & 0xff), int((rr.y >> 16) & 0xff)};
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (ftl[f] == 0) {
+        const R* base = p.nbPtrs != nullptr ? static_cast<const R*>(p.nbPtrs[4 * elem + f])
+                                            : static_cast<const R*>(p.faceProj.at(p.nbIdx[4 * elem + f]));
+        src[f] = base != nullptr ? base + fjl[f] * PRJ : nullptr;
+      }
+    }
+  };
+  auto issue = [&](int slot, const R* s, uint64_t* b, uint32_t extra) {
+    // one arrival per loader lane and barrier phase; `extra`: bytes of a second copy signalled on the same barrier
+    if (s != nullptr) {
+      mbar_arrive_expect_tx(b, PRJ * sizeof(R) + extra);
+      tma_load(myTile + slot * PRJ, s, PRJ * sizeof(R), b);
+    } else {
+      mbar_arrive_expect_tx(b, extra);
+    }
+  };
+
+  long long batch = blockIdx.x;
+  if (batch >= nBatches) {
+    return;
+  }
+  // ---- prologue (exposed once per CTA): metadata of the first batch, tiles of faces 0/1, element ids of the second
+  long long el = active ? slotElem(batch, g) : -1;
+  unsigned hk = faceMeta(el);
+  long long myElem = le >= 0 ? slotElem(batch, le) : -1;
+  const R* src[4];
+  faceSrc(le >= 0 ? myElem : -1, src);
+  if (le >= 0) {
+    issue(0, src[0], bar, 0);
+    issue(1, src[1], bar + 1, 0);
+  }
+  long long elN = active ? slotElem(batch + stride, g) : -1;
+  long long myElemN = le >= 0 ? slotElem(batch + stride, le) : -1;
+  R a[kNQ];
+  auto loadA = [&](long long elem, unsigned meta, int f) {
+    const R* A = elem >= 0 ? static_cast<const R*>(p.neighInt.at(elem)) + 81 * f + 9 * q : nullptr;
+    const bool k = (meta >> (8 + f)) & 1u;
+#pragma unroll
+    for (int c = 0; c < kNQ; ++c) {
+      a[c] = k ? A[c] : R(0);
+    }
+  };
+  loadA(el, hk, 0);
+
+  uint32_t phase = 0;
+  for (; batch < nBatches; batch += stride) {
+    const bool haveNext = batch + stride < nBatches;
+    // tiles of faces 2/3 of THIS batch: their slots staged the previous update, whose bulk store has to be done reading
+    if (le >= 0) {
+      tma_store_wait_read();
+      if (src[2] != nullptr) {
+        mbar_arrive_expect_tx(bar + 2, PRJ * sizeof(R) * (src[3] != nullptr ? 2 : 1));
+        tma_load(myTile + 2 * PRJ, src[2], PRJ * sizeof(R), bar + 2);
+        if (src[3] != nullptr) {
+          tma_load(myTile + 3 * PRJ, src[3], PRJ * sizeof(R), bar + 2);
+        }
+      } else {
+        issue(3, src[3], bar + 2, 0);
+      }
+    }
+    // metadata of the next batch (its element ids arrived a batch ago): consumed at barrier S1
+    const unsigned hkN = faceMeta(elN);
+    const R* srcN[4];
+    faceSrc(le >= 0 ? myElemN : -1, srcN);
+
+    R acc[BP];
+#pragma unroll
+    for (int k = 0; k < BP; ++k) {
+      acc[k] = R(0);
+    }
+    long long elN2 = -1, myElemN2 = -1;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (f < 3) {
+        mbar_wait(bar + f, phase);   // f = 2: slots 2 and 3
+      }
+      // x = column q of (F_nb . AminusT_f)
+      R x[B2P];
+#pragma unroll
+      for (int k = 0; k < B2P; ++k) {
+        x[k] = R(0);
+      }
+      const R* const Fnb = tile + f * PRJ;
+#pragma unroll
+      for (int c = 0; c < kNQ; ++c) {
+#pragma unroll
+        for (int k4 = 0; k4 < B2P / 4; ++k4) {
+          R t[4];
+          ld4(t, Fnb + c * B2P + 4 * k4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            x[4 * k4 + i] = fma(a[c], t[i], x[4 * k4 + i]);
+          }
+        }
+      }
+      // faces without a regular neighbor loaded no tile: x came from stale shared memory -> exact zero (select)
+      const bool keep = (hk >> (8 + f)) & 1u;
+#pragma unroll
+      for (int k = 0; k < B2P; ++k) {
+        x[k] = keep ? x[k] : R(0);
+      }
+      // the flux-solver column of the next face (of the next element after face 3) travels during fPD / rDivM
+      if (f < 3) {
+        loadA(el, hk, f + 1);
+      } else {
+        loadA(elN, hkN, 0);
+      }
+      if (f == 1) {
+        __syncthreads();  // S1: slots 0 and 1 are dead -> the next batch's tiles of faces 0/1
+        if (haveNext && le >= 0) {
+          issue(0, srcN[0], bar, 0);
+          issue(1, srcN[1], bar + 1, 0);
+        }
+      }
+      if (f == 3) {
+        __syncthreads();  // S3: slots 2 and 3 are dead -> they stage the update
+        elN2 = active ? slotElem(batch + 2 * stride, g) : -1;
+        myElemN2 = le >= 0 ? slotElem(batch + 2 * stride, le) : -1;
+      }
+      R F[B2P];
+      G::template fPD<R>(int((hk >> (2 * f)) & 3u), F, x);
+      G::template rDivMr<R>(f, acc, F);
+    }
+
+    // ---- the update leaves as a bulk reduce-add into Q
+    if (active) {
+      R* const col = const_cast<R*>(tile) + P::offStage + q * BP;
+#pragma unroll
+      for (int k4 = 0; k4 < BP / 4; ++k4) {
+        st4(col + 4 * k4, acc[4 * k4], acc[4 * k4 + 1], acc[4 * k4 + 2], acc[4 * k4 + 3]);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (le >= 0 && myElem >= 0) {
+      tmaReduceTensor<R, BP>(static_cast<R*>(const_cast<void*>(p.dofs.at(myElem))), myTile + P::offStage, p.ldg);
+    }
+    // roll over
+    phase ^= 1;
+    el = elN; hk = hkN; myElem = myElemN;
+    elN = elN2; myElemN = myElemN2;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      src[f] = srcN[f];
+    }
+  }
+  if (le >= 0) {
+    tma_store_wait_read();
   }
 }
 

@@ -76,6 +76,45 @@ tma)
 ncufp)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local|k_neigh' --launch-skip 6 -c 3 -f -o $out/full_fp \
       python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_full_fp.log 2>&1 ;;
+g5)
+  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_parity.log 2>&1; echo "exit $?" >> $out/pytest_parity.log
+  timeout 300 python tools/quick_bench.py > $out/qb_base.txt 2>&1
+  SSB_KGEN5=0 timeout 300 python tools/quick_bench.py > $out/qb_gen3.txt 2>&1
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py > $out/qb_$v.txt 2>&1
+  done ;;
+qbv)
+  timeout 300 python tools/quick_bench.py --kernels ader,localwoader,neigh,all > $out/qb_base.txt 2>&1
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py --kernels ader,localwoader,neigh,all > $out/qb_$v.txt 2>&1
+  done ;;
+fp2)
+  timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_parity.log 2>&1; echo "exit $?" >> $out/pytest_parity.log
+  timeout 300 python tools/quick_bench.py --kernels ader,localwoader,neigh,all > $out/qb_base.txt 2>&1
+  SSB_NEIGHFP=1 timeout 300 python tools/quick_bench.py --kernels neigh,all > $out/qb_fp1.txt 2>&1
+  timeout 300 python tools/quick_bench.py --kernels neigh,all --nosort > $out/qb_nosort.txt 2>&1
+  timeout 300 python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all > $out/qb_f64.txt 2>&1
+  SSB_FACEPROJ=0 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all > $out/qb_f64_nofp.txt 2>&1
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py --kernels neigh,all > $out/qb_$v.txt 2>&1
+  done ;;
+pk2)
+  for v in $LSVARIANTS; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_FACEPROJ=0 SSB_LIB=$L timeout 300 python tools/quick_bench.py --kernels ader,localwoader,neigh,all > $out/qb_$v.txt 2>&1
+  done ;;
+f64v)
+  timeout 300 tools/ubench/tma_rate > $out/tma_rate.txt 2>&1
+  SSB_KGEN5=1 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all > $out/qb_f64_g5local.txt 2>&1
+  SSB_KGEN5=3 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all > $out/qb_f64_g5both.txt 2>&1
+  SSB_KGEN=3 timeout 300 python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all > $out/qb_f64_g3.txt 2>&1
+  timeout 300 python tools/quick_bench.py --order 4 --kernels ader,localwoader,neigh,all > $out/qb_o4.txt 2>&1
+  SSB_FACEPROJ=0 SSB_KGEN5=0 timeout 300 python tools/quick_bench.py --order 4 --kernels ader,localwoader,neigh,all > $out/qb_o4_r1.txt 2>&1
+  timeout 300 python tools/quick_bench.py --order 5 --kernels ader,localwoader,neigh,all > $out/qb_o5.txt 2>&1
+  SSB_FACEPROJ=0 SSB_KGEN5=0 timeout 300 python tools/quick_bench.py --order 5 --kernels ader,localwoader,neigh,all > $out/qb_o5_r1.txt 2>&1 ;;
 ubench)
   timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
 qb)

@@ -16,7 +16,8 @@ __device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// mode 0: loads, 1: stores, 2: reduce-add stores.  Every CTA issues `ops` copies of `bytes` per round from `lanes` threads.
+// mode 0: loads, 1: stores, 2: reduce-add stores, 3: loads from RANDOM block addresses (every copy its own random
+// block of `bytes`, like the neighbor gather of the proxy's random topology).  Every CTA issues `ops` copies of `bytes` per round from `lanes` threads.
 template <int MODE>
 __global__ void __launch_bounds__(128) k(char* g, size_t gbytes, int bytes, int ops, int rounds) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -33,7 +34,12 @@ __global__ void __launch_bounds__(128) k(char* g, size_t gbytes, int bytes, int 
     if (tid < ops) {
       char* gp = g + slot * span + (size_t)tid * bytes;
       unsigned char* sp = buf + (size_t)tid * bytes;
-      if (MODE == 0) {
+      if (MODE == 3) {
+        unsigned long long h = (unsigned long long)blockIdx.x * 0x9E3779B97F4A7C15ull + (unsigned long long)r * 0xC2B2AE3D27D4EB4Full + (unsigned long long)tid * 0x165667B19E3779F9ull;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+        gp = g + (h % (gbytes / bytes)) * (size_t)bytes;
+      }
+      if (MODE == 0 || MODE == 3) {
         mbar_expect(bar, bytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sp)), "l"(gp), "r"(bytes), "r"(smem_u32(bar)) : "memory");
       } else if (MODE == 1) {
@@ -46,7 +52,7 @@ __global__ void __launch_bounds__(128) k(char* g, size_t gbytes, int bytes, int 
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
-    if (MODE == 0) { mbar_wait(bar, phase); phase ^= 1; }
+    if (MODE == 0 || MODE == 3) { mbar_wait(bar, phase); phase ^= 1; }
     __syncthreads();
   }
   if (MODE != 0 && tid < ops) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -80,6 +86,7 @@ int main() {
       }
     }
   }
+  for (int c : {2, 4}) for (int s : {256, 864, 2016, 4096}) for (int ops : {28, 64, 112}) run<3>("gather", g, gbytes, s, ops, c);
   for (int s : sizes) for (int ops : {1, 4, 28, 112}) run<1>("store", g, gbytes, s, ops, 2);
   for (int s : sizes) for (int ops : {1, 4, 28, 112}) run<2>("redadd", g, gbytes, s, ops, 2);
   return 0;
