@@ -55,7 +55,8 @@ bool str2kernel(const std::string& s, std::vector<Kernel>& out) {
 struct Flops { double derNz, derHw, volNz, volHw, lfNz, lfHw, nfNz, nfHw; };
 Flops flopsOf(int order) {
   switch (order) {
-    case 4: return {6642, 34146, 4806, 19584, 18972, 0, 4 * 5073.0, 0};
+    case 4: return {6642, 34146, 4806, 19584, 18972, 56448, 4 * 5073.0, 4 * 16992.0};
+    case 5: return {20943, 98001, 13986, 56448, 40320, 102528, 4 * 10671.0, 4 * 29952.0};
     case 6: return {56286, 248292, 34839, 127872, 79200, 246528, 4 * 20805.0, 4 * 73728.0};
     default: return {0, 0, 0, 0, 0, 0, 0, 0};
   }
@@ -118,6 +119,21 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
   upload(p, faceTypes); layer.faceTypes = static_cast<std::uint8_t*>(p);
   upload(p, faceRel); layer.faceRelations = static_cast<std::uint8_t*>(p);
   upload(p, neighbors); layer.faceNeighbors = static_cast<long long*>(p);
+  // face projections (order 6: the neighbor kernel gathers 4 x 864 B per cell instead of 4 x 2016 B; switched off with
+  // SSB_FACEPROJ=0).  Not for the *_dr kernels: their faces are all DynamicRupture.
+  {
+    const char* e = std::getenv("SSB_FACEPROJ");
+    bool useFaceProj = e != nullptr ? e[0] != '0' : order >= 6;
+    for (Kernel k : kernels) {
+      useFaceProj = useFaceProj && (k == Kernel::All || k == Kernel::Local || k == Kernel::Neighbor || k == Kernel::Ader || k == Kernel::LocalWOAder);
+    }
+    if (useFaceProj) {
+      const int b2p = (order * (order + 1) / 2 + 3) / 4 * 4;
+      layer.faceProjectionsStride = static_cast<std::size_t>(4 * 9 * b2p);
+      checkCuda(cudaMalloc(&layer.faceProjections, cells * layer.faceProjectionsStride * sizeof(real)), "cudaMalloc");
+      checkCuda(cudaMemset(layer.faceProjections, 0, cells * layer.faceProjectionsStride * sizeof(real)), "cudaMemset");
+    }
+  }
 
   // processing order of the neighbor kernel: cells grouped by their four (neighbor face, orientation) pairs -- the
   // reference's recorder groups by the same key (NeighIntegrationRecorder.cpp:142-144)
@@ -278,26 +294,55 @@ int run(std::size_t cells, std::size_t timesteps, const std::vector<Kernel>& ker
     if ((k == Kernel::NeighborDR || k == Kernel::AllDR) && order == 6) { nz += 4 * 56387.0; }
   }
   const double total = double(cells) * double(timesteps);
-  const double gnz = nz * total * 1e-9, ghw = hw * total * 1e-9, gib = reals * sizeof(real) * total / (1024.0 * 1024.0 * 1024.0);
+  // `gib`: the reference's legacy estimate with this build's padded tensor sizes (Time.cpp:222-232, Local.cpp:508-520,
+  // Neighbor.cpp:218-226); `gib-kernel`: the algorithmic bytes of SURVEY.md §8(d) (unpadded, what the kernels have to move)
+  double legacy = 0;
+  const double qsz = double(qs);
+  for (Kernel k : kernels) {
+    const bool a = k == Kernel::All || k == Kernel::Local || k == Kernel::Ader || k == Kernel::AllDR;
+    const bool l = k == Kernel::All || k == Kernel::Local || k == Kernel::LocalWOAder || k == Kernel::AllDR;
+    const bool n = k == Kernel::All || k == Kernel::Neighbor;
+    if (a) legacy += 3 * qsz + 72;
+    if (l) legacy += 72 + 4 * 81 + qsz;
+    if (n) legacy += 6 * qsz + 4 * 81;
+  }
+  const double gnz = nz * total * 1e-9, ghw = hw * total * 1e-9;
+  const double gib = legacy * sizeof(real) * total / (1024.0 * 1024.0 * 1024.0);
+  const double gibKernel = reals * sizeof(real) * total / (1024.0 * 1024.0 * 1024.0);
+  const double cycles = 0.0;  // the reference derives cycles from time and always reports 0 (src/Proxy/Tools.cpp:12-40)
   if (!json) {
     std::cout << "=================================================\n";
     std::cout << "===            PERFORMANCE SUMMARY            ===\n";
     std::cout << "=================================================\n";
     std::cout << "seissol proxy mode                  : " << kernelStr << '\n';
     std::cout << "time for seissol proxy              : " << time << '\n';
-    std::cout << "cycles                              : " << 0.0 << '\n' << '\n';
+    std::cout << "cycles                              : " << cycles << '\n' << '\n';
+    std::cout << "GFLOP (libxsmm)                     : " << 0.0 << '\n';
+    std::cout << "GFLOP (pspamm)                      : " << 0.0 << '\n';
+    std::cout << "GFLOP (libxsmm + pspamm)            : " << 0.0 << '\n';
     std::cout << "GFLOP (non-zero) for seissol proxy  : " << gnz << '\n';
     std::cout << "GFLOP (hardware) for seissol proxy  : " << ghw << '\n';
-    std::cout << "GiB (estimate) for seissol proxy    : " << gib << '\n' << '\n';
+    std::cout << "GiB (estimate) for seissol proxy    : " << gib << '\n';
+    std::cout << "GiB (kernels) for seissol proxy     : " << gibKernel << '\n' << '\n';
+    std::cout << "FLOPS/cycle (non-zero)              : " << 0.0 << '\n';
+    std::cout << "FLOPS/cycle (hardware)              : " << 0.0 << '\n';
+    std::cout << "Bytes/cycle (estimate)              : " << 0.0 << '\n';
+    std::cout << "Bytes/cycle (kernel)                : " << 0.0 << '\n' << '\n';
     std::cout << "GFLOPS (non-zero) for seissol proxy : " << gnz / time << '\n';
     std::cout << "GFLOPS (hardware) for seissol proxy : " << ghw / time << '\n';
     std::cout << "GiB/s (estimate) for seissol proxy  : " << gib / time << '\n';
+    std::cout << "GiB/s (kernel) for seissol proxy    : " << gibKernel / time << '\n';
     std::cout << "element updates/s                   : " << total / time << '\n';
     std::cout << "=================================================\n\n";
   } else {
-    std::cout << "{\"name\":\"" << kernelStr << "\",\"time\":" << time << ",\"cycles\":0,\"gflop-nz\":" << gnz
-              << ",\"gflop-hw\":" << ghw << ",\"gib\":" << gib << ",\"gflops-nz\":" << gnz / time << ",\"gflops-hw\":" << ghw / time
-              << ",\"gibs\":" << gib / time << ",\"elem-updates-per-s\":" << total / time << "}\n";
+    // the 17 keys of the reference's JSON line in its order (src/Proxy/Common.cpp:135-151; with cycles = 0 the
+    // reference's per-cycle fields are not finite, they are written as 0 here), then our addition
+    std::cout << "{\"name\":\"" << kernelStr << "\",\"time\":" << time << ",\"cycles\":" << cycles
+              << ",\"gflop-libxsmm\":0,\"gflop-pspamm\":0,\"gflop-nz\":" << gnz << ",\"gflop-hw\":" << ghw
+              << ",\"gib\":" << gib << ",\"gib-kernel\":" << gibKernel
+              << ",\"gflopcycle-nz\":0,\"gflopcycle-hw\":0,\"gibcycle\":0,\"gibcycle-kernel\":0"
+              << ",\"gflops-nz\":" << gnz / time << ",\"gflops-hw\":" << ghw / time << ",\"gibs\":" << gib / time
+              << ",\"gibs-kernel\":" << gibKernel / time << ",\"elem-updates-per-s\":" << total / time << "}\n";
   }
   if (!dump.empty()) {
     std::vector<real> out(cells * qs);

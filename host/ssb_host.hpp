@@ -84,6 +84,10 @@ struct Layer {
   long long* faceNeighbors{nullptr};      // [size][4] index into buffers (proxy) ...
   const void* const* faceNeighborPtrs{nullptr};  // ... or LTS::FaceNeighborsDevice pointers
   int* permutation{nullptr};              // optional processing order of the neighbor kernel
+  // optional face projections F_f = fMrT_f I, [size][4][9][B2P] (include/seissol_b200.h "face-projection path"): when
+  // set, Local stores them and Neighbor gathers them (faceNeighbors then index this array) instead of the neighbors' I
+  void* faceProjections{nullptr};
+  std::size_t faceProjectionsStride{0};   // reals per cell
   std::size_t dofsStride{0}, derivativesStride{0};  // reals per cell
 };
 
@@ -130,6 +134,14 @@ class Local {
   explicit Local(Context& ctx) : ctx_(ctx) {}
   void computeBatchedIntegral(Layer& layer, double /*timeStepWidth*/, cudaStream_t stream) {
     const std::size_t rs = layer.realSize;
+    if (layer.faceProjections != nullptr) {
+      check(ssb_local_faceproj(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs),
+                               strided(layer.buffers, layer.dofsStride * rs), strided(layer.localIntegration, 396 * rs),
+                               strided(layer.faceProjections, layer.faceProjectionsStride * rs), layer.faceTypes,
+                               static_cast<long long>(layer.size), nullptr, stream),
+            "ssb_local_faceproj");
+      return;
+    }
     check(ssb_local(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), strided(layer.buffers, layer.dofsStride * rs),
                     strided(layer.localIntegration, 396 * rs), layer.faceTypes, static_cast<long long>(layer.size), nullptr,
                     stream),
@@ -145,6 +157,14 @@ class Neighbor {
   explicit Neighbor(Context& ctx) : ctx_(ctx) {}
   void computeBatchedNeighborsIntegral(Layer& layer, cudaStream_t stream) {
     const std::size_t rs = layer.realSize;
+    if (layer.faceProjections != nullptr && layer.faceNeighborPtrs == nullptr) {
+      check(ssb_neigh_faceproj(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), nullptr, layer.faceNeighbors,
+                               strided(layer.faceProjections, layer.faceProjectionsStride * rs),
+                               strided(layer.neighboringIntegration, 324 * rs), layer.faceTypes, layer.faceRelations,
+                               static_cast<long long>(layer.size), layer.permutation, stream),
+            "ssb_neigh_faceproj");
+      return;
+    }
     check(ssb_neigh(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), layer.faceNeighborPtrs, layer.faceNeighbors,
                     strided(layer.buffers, layer.dofsStride * rs), strided(layer.neighboringIntegration, 324 * rs),
                     layer.faceTypes, layer.faceRelations, static_cast<long long>(layer.size), layer.permutation, stream),

@@ -9,6 +9,14 @@
  * allocation), matching how the reference enqueues work on StreamRuntime::stream()
  * (src/Parallel/Runtime/Stream.h:163-190).
  *
+ * Devices and threads: an entry point launches on the CURRENT CUDA device of the calling thread (the device the
+ * stream and all pointers must belong to); one-time kernel attributes are set per device on first use, so one process
+ * may drive several GPUs.  A context holds no device state and may be shared by host threads; calls on one stream
+ * must not be issued concurrently.
+ * Alignment: every per-element block (base + i*stride, or pointer-table entry) must be 16-byte aligned -- the kernels
+ * move them with cp.async.bulk and 128-bit accesses; misaligned strided arrays are rejected with SSB_EINVAL, pointer
+ * table entries are the caller's responsibility.  face_types rows are read as 4-byte, face_rel rows as 8-byte words.
+ *
  * Return value: 0 on success, a positive cudaError_t code from the launch, or a
  * negative SSB_E* code for invalid arguments.  There is NO CPU fallback: without a
  * usable CUDA device every compute entry point fails.
@@ -121,6 +129,18 @@ int ssb_ader_local_faceproj(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, s
 int ssb_neigh_faceproj(ssb_ctx* ctx, ssb_array_t dofs, const void* const* nb_ptrs, const long long* nb_idx,
                        ssb_array_t face_proj, ssb_array_t neigh_int, const uint8_t* face_types,
                        const uint8_t* face_rel, long long n, const int* perm, void* stream);
+
+/* LTS with face projections.  ssb_taylor_faceproj: for a neighbor that is read through its derivative family
+ * (LtsSetup::neighborHasDerivatives, src/Initializer/LtsSetup.h:21-111; TimeCommon::computeBatchedIntegrals,
+ * src/Kernels/TimeCommon.cpp:89-125) integrate the family over the reader's interval (coeffs as ssb_taylor) and store
+ * F = fMrT_j I of the one face j (face_j: device uint8 [n]) the reader sees: proj_out entries are [9][B2P] blocks.  The
+ * neighbor table of ssb_neigh_faceproj then holds (block pointer - j * 9 * B2P reals) for such faces.
+ * ssb_accumulate_rows: dst = reset ? src : dst + src on rows of reals_per_row reals (multiple of 4) -- the buffer
+ * accumulation of ssb_lts_accumulate for face-projection rows. */
+int ssb_taylor_faceproj(ssb_ctx* ctx, ssb_array_t derivs, ssb_array_t proj_out, const uint8_t* face_j,
+                        const double* coeffs, long long n, void* stream);
+int ssb_accumulate_rows(ssb_ctx* ctx, ssb_array_t dst, ssb_array_t src, int reset, long long n, int reals_per_row,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dynamic rupture.  Fault tensors use the reference's layout: point index fastest, padded to

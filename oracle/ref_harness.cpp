@@ -395,4 +395,15 @@ int ssref_threads() {
   return 1;
 #endif
 }
+
+// torchrun exports OMP_NUM_THREADS=1 to every rank: the benchmark's reference arm asks for all host cores explicitly
+void ssref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) {
+    omp_set_num_threads(n);
+  }
+#else
+  (void)n;
+#endif
+}
 }

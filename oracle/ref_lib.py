@@ -178,6 +178,29 @@ class RefLib:
     def threads(self):
         return int(self.lib.ssref_threads())
 
+    def set_threads(self, n):
+        """OpenMP threads of the reference kernels (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+        self.lib.ssref_set_threads(ctypes.c_int(int(n)))
+        return self.threads()
+
+    def dr_interpolate_timed(self, ders_plus, ders_minus, tinvT, face_info, coeffs, passes=1):
+        """Seconds per pass of the reference's batched space-time interpolation on the host cores (no layout conversion
+        inside the timed region)."""
+        import time
+        n = ders_plus[0].shape[0]
+        dp, dm = self.ders_to_ref(ders_plus), self.ders_to_ref(ders_minus)
+        t = np.ascontiguousarray(tinvT.transpose(0, 2, 1), dtype=self.dtype)
+        fi = np.ascontiguousarray(face_info, dtype=np.uint8)
+        c = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        qp = np.zeros((n, self.order, self.qinterp), dtype=self.dtype)
+        qm = np.zeros_like(qp)
+        args = (ctypes.c_int64(n), _p(dp), _p(dm), _p(t), _p(fi), _p(c), _p(qp), _p(qm))
+        self.lib.ssref_dr_interp(*args)
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            self.lib.ssref_dr_interp(*args)
+        return (time.perf_counter() - t0) / passes
+
 
 class ViscoRefLib:
     """The reference's generated viscoelastic2 kernels (oracle/ref_harness_visco.cpp).  Arrays cross in the
@@ -250,7 +273,11 @@ class ViscoRefLib:
         return self.from_ref(q), self.ane_from_ref(qa)
 
     def threads(self):
-        return os.cpu_count() or 1
+        return int(self.lib.ssrefv_threads())
+
+    def set_threads(self, n):
+        self.lib.ssrefv_set_threads(ctypes.c_int(int(n)))
+        return self.threads()
 
     def proxy_all(self, d, coeffs, passes):
         """Proxy `all` on the host cores; returns (seconds, Q, Qane)."""

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(HERE, "lib", "libseissol_b2
 SYMBOLS = [
     "ssb_create", "ssb_destroy", "ssb_set_layout", "ssb_layout_reference", "ssb_query",
     "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_lts_accumulate", "ssb_neigh",
-    "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj",
+    "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj", "ssb_taylor_faceproj", "ssb_accumulate_rows",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh",
     "ssb_error_string", "ssb_version",
@@ -84,6 +84,8 @@ def load_library():
     lib.ssb_local_faceproj.argtypes = [P, A, A, A, A, P, LL, P, P]
     lib.ssb_ader_local_faceproj.argtypes = [P, A, A, A, A, A, P, P, LL, P, P]
     lib.ssb_neigh_faceproj.argtypes = [P, A, P, P, A, A, P, P, LL, P, P]
+    lib.ssb_taylor_faceproj.argtypes = [P, A, A, P, P, LL, P]
+    lib.ssb_accumulate_rows.argtypes = [P, A, A, I, LL, I, P]
     lib.ssb_set_dr_layout.argtypes = [P, I]
     lib.ssb_dr_interp.argtypes = [P, A, A, P, P, P, P, P, LL, P, P]
     lib.ssb_friction_lsw.argtypes = [P, ctypes.POINTER(SsbFrictionData), ctypes.POINTER(SsbFrictionParams), LL, P]
@@ -101,9 +103,18 @@ def _check(code):
         raise SsbError(f"seissol_b200 error {code}: {load_library().ssb_error_string(code).decode()}")
 
 
+def _check_device(t):
+    """The entry points launch on the CURRENT device (include/seissol_b200.h): the tensors must live there."""
+    import torch
+    if t.device.index != torch.cuda.current_device():
+        raise SsbError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                       "call torch.cuda.set_device / use a torch.cuda.device guard around the seissol_b200 calls")
+
+
 def strided(t):
     """torch tensor [n, ...] (contiguous, on the GPU) -> base + stride descriptor."""
     assert t.is_cuda and t.is_contiguous()
+    _check_device(t)
     stride = t.stride(0) * t.element_size() if t.dim() > 0 and t.shape[0] > 0 else 0
     return SsbArray(None, t.data_ptr(), stride)
 
@@ -111,6 +122,7 @@ def strided(t):
 def pointer_table(t):
     """torch int64 tensor of device pointers (the reference's `real**` tables)."""
     assert t.is_cuda and t.dtype.is_floating_point is False
+    _check_device(t)
     return SsbArray(t.data_ptr(), None, 0)
 
 
@@ -209,6 +221,13 @@ class Context:
         _check(self.lib.ssb_neigh_faceproj(self.handle, dofs, _ptr(nb_ptrs), _ptr(nb_idx),
                                            face_proj if face_proj is not None else NONE, neigh_int,
                                            _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
+
+    def taylor_faceproj(self, derivs, proj_out, face_j, coeffs, n, stream=None):
+        keep, c = self._coeffs(coeffs)
+        _check(self.lib.ssb_taylor_faceproj(self.handle, derivs, proj_out, _ptr(face_j), c, n, _stream(stream)))
+
+    def accumulate_rows(self, dst, src, reset, n, reals_per_row, stream=None):
+        _check(self.lib.ssb_accumulate_rows(self.handle, dst, src, 1 if reset else 0, n, reals_per_row, _stream(stream)))
 
     # -- viscoelastic2 --------------------------------------------------------------------------
     def visco_ader(self, dofs, dofs_ane, idofs, idofs_ane, local_int, coeffs, n, stream=None):

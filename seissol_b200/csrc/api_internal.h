@@ -6,7 +6,55 @@
 
 #include "params.cuh"
 
+#include <atomic>
+
 namespace ssb {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies to the CURRENT device only: every launcher keeps one slot per
+// device ordinal (a host may drive several GPUs from one process) and raises the attribute when a launch needs more.
+// The slots are atomics: two host threads racing on the first launch both set the same value.
+struct SmemConfig {
+  std::atomic<size_t> bytes[64];
+  SmemConfig() {
+    for (auto& b : bytes) {
+      b.store(0);
+    }
+  }
+};
+template <typename Kernel>
+inline int ensureDynamicSmem(Kernel kern, size_t bytes, SmemConfig& cfg) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    return int(cudaGetLastError());
+  }
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && cfg.bytes[dev].load(std::memory_order_acquire) >= bytes && bytes > 0) {
+    return 0;
+  }
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (err != cudaSuccess) {
+    return int(err);
+  }
+  if (tracked) {
+    cfg.bytes[dev].store(bytes, std::memory_order_release);
+  }
+  return 0;
+}
+// SM count of the CURRENT device (cached per device ordinal)
+inline int smCountOfCurrentDevice() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < 64;
+  int sms = tracked ? cache[dev].load() : 0;
+  if (sms == 0) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (tracked) {
+      cache[dev].store(sms);
+    }
+  }
+  return sms;
+}
 
 struct KernelSet {
   int order;
@@ -19,6 +67,7 @@ struct KernelSet {
   int (*neigh)(const NeighParams&, cudaStream_t);
   int (*taylor)(const TaylorParams&, cudaStream_t);
   int (*accumulate)(const AccumulateParams&, cudaStream_t);
+  int (*taylorFp)(const TaylorParams&, cudaStream_t);   // Taylor sum + face projection (full-column units only)
 };
 
 struct DrKernelSet {

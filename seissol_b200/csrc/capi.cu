@@ -1,5 +1,6 @@
 // C ABI of libseissol_b200.so (declared in include/seissol_b200.h).  Thin argument
 // validation + dispatch onto the per-(order, real) kernel instantiations.  No CPU path.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +57,15 @@ void referenceLayout(ssb_ctx* c) {
     off += 9 * ld;
   }
   c->derSize = off;
+}
+
+// strided arrays: base and stride must be 16-byte aligned (bulk copies, 128-bit accesses); pointer tables cannot be
+// checked on the host
+bool aligned16(const ssb_array_t& a) {
+  if (a.ptrs != nullptr || a.base == nullptr) {
+    return true;
+  }
+  return reinterpret_cast<uintptr_t>(a.base) % 16 == 0 && a.stride_bytes % 16 == 0;
 }
 
 ElemArray conv(const ssb_array_t& a) {
@@ -158,6 +168,9 @@ int fillLocal(ssb_ctx* c, LocalParams& p, ssb_array_t dofs, ssb_array_t idofs, s
   if (!p.dofs.present() || !p.idofs.present() || !p.localInt.present()) {
     return SSB_EINVAL;
   }
+  if (!aligned16(dofs) || !aligned16(idofs) || !aligned16(derivs) || !aligned16(localInt)) {
+    return SSB_EINVAL;
+  }
   p.faceTypes = faceTypes;
   p.perm = perm;
   p.n = n;
@@ -236,6 +249,10 @@ int ssb_set_layout(ssb_ctx* c, int ld_q, const int* der_offset, const int* der_l
     int end = 0;
     for (int d = 0; d < c->order; ++d) {
       if (der_ld[d] % 4 != 0 || der_offset[d] % 4 != 0 || der_ld[d] < (basisFunctions(c->order - d) + 3) / 4 * 4) {
+        return SSB_EINVAL;
+      }
+      // the family is moved as ONE block [0, end): the dQ(d) must follow each other without overlap
+      if (der_offset[d] < end) {
         return SSB_EINVAL;
       }
       c->derOffset[d] = der_offset[d];
@@ -370,6 +387,9 @@ int ssb_neigh_faceproj(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs,
       (nb_ptrs == nullptr && (nb_idx == nullptr || !p.faceProj.present()))) {
     return SSB_EINVAL;
   }
+  if (!aligned16(dofs) || !aligned16(face_proj) || !aligned16(neigh_int)) {
+    return SSB_EINVAL;
+  }
   p.useFaceProj = 1;
   p.faceTypes = face_types;
   p.faceRel = face_rel;
@@ -392,7 +412,7 @@ int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* 
   if (n == 0) {
     return 0;
   }
-  if (!p.derivs.present() || !p.idofs.present()) {
+  if (!p.derivs.present() || !p.idofs.present() || !aligned16(derivs) || !aligned16(idofs)) {
     return SSB_EINVAL;
   }
   p.n = n;
@@ -406,6 +426,56 @@ int ssb_taylor(ssb_ctx* c, ssb_array_t derivs, ssb_array_t idofs, const double* 
     p.coeffs[d] = coeffs[d];
   }
   return c->ks->taylor(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_taylor_faceproj(ssb_ctx* c, ssb_array_t derivs, ssb_array_t proj_out, const uint8_t* face_j,
+                        const double* coeffs, long long n, void* stream) {
+  if (c == nullptr || coeffs == nullptr || n < 0 || c->ks->taylorFp == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  TaylorParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.derivs = conv(derivs);
+  p.idofs = conv(proj_out);
+  p.faceJ = face_j;
+  if (!p.derivs.present() || !p.idofs.present() || face_j == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.n = n;
+  p.ldg = c->ldq;
+  p.order = c->order;
+  p.derSize = c->derSize;
+  for (int d = 0; d < c->order; ++d) {
+    p.rows[d] = basisFunctions(c->order - d);
+    p.derOffset[d] = c->derOffset[d];
+    p.derLd[d] = c->derLd[d];
+    p.coeffs[d] = coeffs[d];
+  }
+  return c->ks->taylorFp(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_accumulate_rows(ssb_ctx* c, ssb_array_t dst, ssb_array_t src, int reset, long long n, int reals_per_row,
+                        void* stream) {
+  if (c == nullptr || n < 0 || reals_per_row <= 0 || reals_per_row % 4 != 0) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  AccumulateParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.buffers = conv(dst);
+  p.idofs = conv(src);
+  if (!p.buffers.present() || !p.idofs.present()) {
+    return SSB_EINVAL;
+  }
+  p.n = n;
+  p.vec4PerElem = reals_per_row / 4;
+  p.reset = reset;
+  return c->ks->accumulate(p, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_lts_accumulate(ssb_ctx* c, ssb_array_t buffers, ssb_array_t idofs, int reset, long long n, void* stream) {
@@ -448,6 +518,9 @@ int ssb_neigh(ssb_ctx* c, ssb_array_t dofs, const void* const* nb_ptrs, const lo
       (nb_ptrs == nullptr && (nb_idx == nullptr || !p.idofs.present()))) {
     return SSB_EINVAL;
   }
+  if (!aligned16(dofs) || !aligned16(idofs) || !aligned16(neigh_int)) {
+    return SSB_EINVAL;
+  }
   p.faceTypes = face_types;
   p.faceRel = face_rel;
   p.perm = perm;
@@ -478,7 +551,7 @@ int ssb_dr_interp(ssb_ctx* c, ssb_array_t der_plus, ssb_array_t der_minus, const
   p.derPlus = conv(der_plus);
   p.derMinus = conv(der_minus);
   if (!p.derPlus.present() || !p.derMinus.present() || tinv_t == nullptr || face_info == nullptr ||
-      q_plus == nullptr || q_minus == nullptr) {
+      q_plus == nullptr || q_minus == nullptr || !aligned16(der_plus) || !aligned16(der_minus)) {
     return SSB_EINVAL;
   }
   p.tinvT = tinv_t;

@@ -18,14 +18,11 @@ namespace {
 // grid size: one CTA per batch, or (SSB_PERSISTENT=k) k CTAs per SM walking the batches in lock step
 inline unsigned gridFor(long long batches) {
   static int persistent = -1;
-  static int sms = 0;
   if (persistent < 0) {
     const char* e = std::getenv("SSB_PERSISTENT");
     persistent = e != nullptr ? std::atoi(e) : 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int sms = persistent > 0 ? smCountOfCurrentDevice() : 0;
   if (persistent > 0 && batches > static_cast<long long>(persistent) * sms) {
     return static_cast<unsigned>(persistent * sms);
   }
@@ -43,23 +40,7 @@ inline size_t smemPad() {
   return static_cast<size_t>(pad);
 }
 
-// SM count of the CURRENT device (cached per device ordinal)
-inline int smCount() {
-  static int cache[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) {
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-  }
-  if (cache[dev] == 0) {
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cache[dev] = sms;
-  }
-  return cache[dev];
-}
+inline int smCount() { return smCountOfCurrentDevice(); }
 
 // Traits binding the generated operator code of one order to the kernel templates.
 struct Gen {
@@ -130,17 +111,9 @@ template <bool ADER>
 int launchLocal5(const LocalParams& p, cudaStream_t stream) {
   using P = LocalPlan<Real, Gen, EL>;
   auto kern = ADER ? k_ader5<Real, Gen, EL> : k_local5<Real, Gen, EL>;
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    if (dev >= 0 && dev < 64) {
-      configured[dev] = true;
-    }
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes + smemPad(), smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -157,13 +130,9 @@ template <bool ADER, bool LOCAL>
 int launchLocal(const LocalParams& p, cudaStream_t stream) {
   using P = LocalPlan<Real, Gen, EL>;
   auto kern = k_local<Real, Gen, EL, ADER, LOCAL>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = true;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes + smemPad(), smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -231,17 +200,9 @@ inline int neighFpGeneration() {
 int neighFp2Entry(const NeighParams& p, cudaStream_t stream) {
   using P = NeighFp2Plan<Real, Gen, ENF2>;
   auto kern = k_neigh_fp2<Real, Gen, ENF2>;
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    if (dev >= 0 && dev < 64) {
-      configured[dev] = true;
-    }
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes + smemPad(), smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -261,13 +222,9 @@ int neighFpEntry(const NeighParams& p, cudaStream_t stream) {
   }
   using P = NeighFpPlan<Real, Gen, ENF>;
   auto kern = k_neigh_fp<Real, Gen, ENF>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = true;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes + smemPad(), smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -286,13 +243,9 @@ int neighEntry(const NeighParams& p, cudaStream_t stream) {
   }
   using P = NeighPlan<Real, Gen, EN>;
   auto kern = k_neigh<Real, Gen, EN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes + smemPad()));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = true;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes + smemPad(), smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -307,16 +260,29 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
     return 0;
   }
   const size_t bytes = (size_t(kTaylorE) * (p.derSize + kNQ * p.ldg) * sizeof(Real) + 15) / 16 * 16 + 16;
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t err = cudaFuncSetAttribute(k_taylor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = bytes;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(k_taylor<Real>, bytes, smemConfig)) {
+    return rc;
   }
   k_taylor<Real><<<unsigned((p.n + kTaylorE - 1) / kTaylorE), 256, bytes, stream>>>(p);
   return int(cudaGetLastError());
+}
+
+int taylorFpEntry(const TaylorParams& p, cudaStream_t stream) {
+#if SSB_PACK_F32 == 1
+  if (p.n <= 0) {
+    return 0;
+  }
+  const size_t bytes = (size_t(kTaylorFpE) * (p.derSize + kNQ * Gen::kBP + kNQ * Gen::kB2P) * sizeof(Real) + 15) / 16 * 16 + 16;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(k_taylor_fp<Real, Gen>, bytes, smemConfig)) {
+    return rc;
+  }
+  k_taylor_fp<Real, Gen><<<unsigned((p.n + kTaylorFpE - 1) / kTaylorFpE), 256, bytes, stream>>>(p);
+  return int(cudaGetLastError());
+#else
+  return -2;
+#endif
 }
 
 int accumulateEntry(const AccumulateParams& p, cudaStream_t stream) {
@@ -331,7 +297,7 @@ int accumulateEntry(const AccumulateParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
-const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry, accumulateEntry};
+const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry, accumulateEntry, taylorFpEntry};
 
 }  // namespace
 

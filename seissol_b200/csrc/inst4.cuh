@@ -54,14 +54,11 @@ constexpr int VL = Pk<Real>::V;
 
 inline unsigned gridFor4(long long batches) {
   static int persistent = -1;
-  static int sms = 0;
   if (persistent < 0) {
     const char* e = std::getenv("SSB_PERSISTENT");
     persistent = e != nullptr ? std::atoi(e) : 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int sms = persistent > 0 ? smCountOfCurrentDevice() : 0;
   if (persistent > 0 && batches > static_cast<long long>(persistent) * sms) {
     return static_cast<unsigned>(persistent * sms);
   }
@@ -72,13 +69,9 @@ template <bool ADER, bool LOCAL>
 int launchLocal(const LocalParams& p, cudaStream_t stream) {
   using P = LocalPlan<Real, Gen, NP>;
   auto kern = k_local4<Real, Gen, NP, ADER, LOCAL>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = true;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes, smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -101,13 +94,9 @@ int localEntry(const LocalParams& p, bool ader, bool local, cudaStream_t stream)
 int neighEntry(const NeighParams& p, cudaStream_t stream) {
   using P = NeighPlan<Real, Gen, NP>;
   auto kern = k_neigh4<Real, Gen, NP>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P::bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = true;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, P::bytes, smemConfig)) {
+    return rc;
   }
   if (p.n <= 0) {
     return 0;
@@ -122,13 +111,9 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
     return 0;
   }
   const size_t bytes = (size_t(kTaylorE) * (p.derSize + kNQ * p.ldg) * sizeof(Real) + 15) / 16 * 16 + 16;
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t err = cudaFuncSetAttribute(k_taylor<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = bytes;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(k_taylor<Real>, bytes, smemConfig)) {
+    return rc;
   }
   k_taylor<Real><<<unsigned((p.n + kTaylorE - 1) / kTaylorE), 256, bytes, stream>>>(p);
   return int(cudaGetLastError());

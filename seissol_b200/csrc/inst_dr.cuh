@@ -34,15 +34,8 @@ constexpr int NF = sizeof(SSB_REAL) == 8 ? 4 : 8;  // faces per CTA (k_dr_interp
 constexpr int NDW = sizeof(SSB_REAL) == 8 ? 4 : 8;  // warps = elements per CTA (k_neigh_dr); static shared memory <= 48 KB
 
 template <typename K>
-int setSmem(K kern, size_t bytes, size_t& configured) {
-  if (bytes > configured) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    configured = bytes;
-  }
-  return 0;
+int setSmem(K kern, size_t bytes, SmemConfig& configured) {
+  return ensureDynamicSmem(kern, bytes, configured);
 }
 
 int drInterpEntry(DrInterpParams& p, cudaStream_t stream) {
@@ -52,7 +45,7 @@ int drInterpEntry(DrInterpParams& p, cudaStream_t stream) {
   auto kern = k_dr_interp<Real, GenO, GenDr, NF>;
   p.rawStride = padOdd16(p.derSize, sizeof(Real));
   const size_t bytes = ((size_t(NF) * (2 * p.rawStride + 84) * sizeof(Real) + 15) / 16) * 16 + 16;
-  static size_t configured = 0;
+  static SmemConfig configured;
   if (int rc = setSmem(kern, bytes, configured)) {
     return rc;
   }

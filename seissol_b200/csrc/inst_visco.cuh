@@ -44,19 +44,12 @@ constexpr int VE = SSB_VE;
 using Plan = ViscoPlan<Real, Gen, VE>;
 
 template <typename K>
-int configure(K kern, size_t bytes, bool& done) {
-  if (!done) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    if (err != cudaSuccess) {
-      return int(err);
-    }
-    done = true;
-  }
-  return 0;
+int configure(K kern, size_t bytes, SmemConfig& done) {
+  return ensureDynamicSmem(kern, bytes, done);
 }
 
 int aderEntry(const ViscoLocalParams& p, cudaStream_t stream) {
-  static bool done = false;
+  static SmemConfig done;
   auto kern = k_visco_ader<Real, Gen, VE>;
   const size_t bytes = Plan::bytes(Plan::aderReals);
   if (int rc = configure(kern, bytes, done)) {
@@ -70,7 +63,7 @@ int aderEntry(const ViscoLocalParams& p, cudaStream_t stream) {
 }
 
 int localEntry(const ViscoLocalParams& p, cudaStream_t stream) {
-  static bool done = false;
+  static SmemConfig done;
   auto kern = k_visco_local<Real, Gen, VE>;
   const size_t bytes = Plan::bytes(Plan::localReals);
   if (int rc = configure(kern, bytes, done)) {
@@ -84,7 +77,7 @@ int localEntry(const ViscoLocalParams& p, cudaStream_t stream) {
 }
 
 int neighEntry(const ViscoNeighParams& p, cudaStream_t stream) {
-  static bool done = false;
+  static SmemConfig done;
   auto kern = k_visco_neigh<Real, Gen, VE>;
   const size_t bytes = Plan::bytes(Plan::neighReals);
   if (int rc = configure(kern, bytes, done)) {

@@ -640,6 +640,9 @@ __global__ void __launch_bounds__(blockThreads(NP), SSB_MINB_NEIGH) k_neigh(cons
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         keep[v] = ft[v][f] == 0;
+        if (p.nbPtrs != nullptr && el[v] >= 0) {
+          keep[v] = keep[v] && p.nbPtrs[4 * el[v] + f] != nullptr;   // a NULL FaceNeighbors entry loads no tile either
+        }
       }
 #pragma unroll
       for (int i = 0; i < B2P; ++i) {

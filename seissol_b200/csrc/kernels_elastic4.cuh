@@ -413,6 +413,14 @@ __device__ __forceinline__ void neighBody4(const NeighParams& p, unsigned char* 
           ft = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el[v]);
         }
         ftReg[v] = (ft.x == 0 ? 1u : 0u) | (ft.y == 0 ? 2u : 0u) | (ft.z == 0 ? 4u : 0u) | (ft.w == 0 ? 8u : 0u);
+        if (p.nbPtrs != nullptr) {   // a NULL FaceNeighbors entry loads no tile: treat the face like a non-regular one
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            if (p.nbPtrs[4 * el[v] + f] == nullptr) {
+              ftReg[v] &= ~(1u << f);
+            }
+          }
+        }
         const uint2 rr = *reinterpret_cast<const uint2*>(p.faceRel + 8 * el[v]);
         relJ[v] = (rr.x & 3u) | (((rr.x >> 16) & 3u) << 2) | ((rr.y & 3u) << 4) | (((rr.y >> 16) & 3u) << 6);
         relH[v] = ((rr.x >> 8) & 3u) | (((rr.x >> 24) & 3u) << 2) | (((rr.y >> 8) & 3u) << 4) | (((rr.y >> 24) & 3u) << 6);

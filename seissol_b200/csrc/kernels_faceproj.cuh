@@ -205,6 +205,87 @@ __global__ void __launch_bounds__((NeighFpPlan<R, G, E>::threads), SSB_MINB_NEIG
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Taylor sum + face projection for LTS neighbors that are read through their derivatives (src/Kernels/TimeCommon.cpp:89-125,
+// Time::evaluateBatched Time.cpp:257-292): I = sum_d c_d dQ(d) of the NEIGHBOR's family over the reader's (sub-)interval,
+// then F = fMrT_j I for the one face j the reader sees -- the block the face-projection neighbor kernel gathers.
+// One item per (cell, face) that needs it; E items per CTA; the family arrives by one bulk copy, I lives in shared memory.
+constexpr int kTaylorFpE = 8;
+template <typename R, typename G>
+__global__ void __launch_bounds__(256) k_taylor_fp(const TaylorParams p) {
+  constexpr int E = kTaylorFpE;
+  constexpr int BP = G::kBP, B2P = G::kB2P, PRJ = kNQ * B2P;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  R* const smem = reinterpret_cast<R*>(smemRaw);
+  const int tenI = kNQ * BP;
+  const int per = p.derSize + tenI + PRJ;                  // reals per item: family | I | projection
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smemRaw + (size_t(E) * per * sizeof(R) + 15) / 16 * 16);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, E);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long first = static_cast<long long>(blockIdx.x) * E;
+  if (tid < E) {
+    const long long el = first + tid;
+    if (el < p.n) {
+      mbar_arrive_expect_tx(bar, p.derSize * sizeof(R));
+      tma_load(smem + tid * per, p.derivs.at(el), p.derSize * sizeof(R), bar);
+    } else {
+      mbar_arrive_expect_tx(bar, 0);
+    }
+  }
+  mbar_wait(bar, 0);
+  // ---- I = sum_d c_d dQ(d), column-major [9][BP] behind the family
+  const int vecPerCol = BP / 4;
+  const int items = E * kNQ * vecPerCol;
+  for (int i = tid; i < items; i += 256) {
+    const int e = i / (kNQ * vecPerCol);
+    const int rem = i - e * (kNQ * vecPerCol);
+    const int c = rem / vecPerCol;
+    const int k0 = 4 * (rem - c * vecPerCol);
+    const R* der = smem + e * per;
+    R out[4] = {R(0), R(0), R(0), R(0)};
+    if (first + e < p.n) {
+      for (int d = 0; d < p.order; ++d) {
+        if (k0 < p.rows[d]) {
+          R t[4];
+          ld4(t, der + p.derOffset[d] + c * p.derLd[d] + k0);
+          const R cd = static_cast<R>(p.coeffs[d]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            out[j] = (k0 + j < p.rows[d]) ? fma(cd, t[j], out[j]) : out[j];
+          }
+        }
+      }
+    }
+    st4(smem + e * per + p.derSize + c * BP + k0, out[0], out[1], out[2], out[3]);
+  }
+  __syncthreads();
+  // ---- F = fMrT_j . I: thread (e, q) owns column q
+  if (tid < E * kNQ) {
+    const int e = tid / kNQ, q = tid - e * kNQ;
+    if (first + e < p.n) {
+      const int j = p.faceJ[first + e];
+      R F[B2P];
+      G::template fMrT<R>(j, F, SrcPk<R>{smem + e * per + p.derSize + q * BP});
+      R* dst = smem + e * per + p.derSize + tenI + q * B2P;
+#pragma unroll
+      for (int k4 = 0; k4 < B2P / 4; ++k4) {
+        st4(dst + 4 * k4, F[4 * k4], F[4 * k4 + 1], F[4 * k4 + 2], F[4 * k4 + 3]);
+      }
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  if (tid < E && first + tid < p.n) {
+    tma_store(const_cast<void*>(p.idofs.at(first + tid)), smem + tid * per + p.derSize + tenI, PRJ * sizeof(R));
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+}
+
 // =======================================================================================================================
 // k_neigh_fp2: the same product as k_neigh_fp on PERSISTENT, SOFTWARE-PIPELINED CTAs.
 //

@@ -40,7 +40,8 @@ struct NeighParams {
 
 struct TaylorParams {
   ElemArray derivs;
-  ElemArray idofs;
+  ElemArray idofs;       // out: I (k_taylor) or the face projection fMrT_j I, [9][B2P] (k_taylor_fp)
+  const uint8_t* faceJ;  // k_taylor_fp: [n] local face id j of the element whose derivatives are integrated
   long long n;
   int ldg;
   int order;
@@ -56,7 +57,7 @@ struct AccumulateParams {
   ElemArray buffers;
   ElemArray idofs;
   long long n;
-  int vec4PerElem;  // tensor size / 4 reals
+  int vec4PerElem;  // row size / 4 reals
   int reset;
 };
 

@@ -89,28 +89,51 @@ class MeshData:
 
 
 class CudaBackend:
-    """The element-update kernels through the C ABI (seissol_b200/api.py) on sub-ranges of the own cells."""
+    """The element-update kernels through the C ABI (seissol_b200/api.py) on sub-ranges of the own cells.
 
-    def __init__(self, ctx, data, coeffs):
+    faceproj (default at order >= 6, SSB_FACEPROJ=0 switches it off): the local kernel stores the face projections
+    F_f = fMrT_f I of every own cell, the neighbor kernel gathers those blocks, and the halo carries the copy cells'
+    face projections instead of their time-integrated DOFs (`halo_tensor`)."""
+
+    def __init__(self, ctx, data, coeffs, faceproj=None):
+        import os
         from . import api
         self.api, self.ctx, self.d, self.coeffs = api, ctx, data, coeffs
+        if faceproj is None:
+            faceproj = os.environ.get("SSB_FACEPROJ", "1" if ctx.order >= 6 else "0") != "0"
+        self.faceproj = bool(faceproj)
+        if self.faceproj and getattr(data, "face_proj", None) is None:
+            data.face_proj = data.torch.zeros((data.buffers.shape[0], ctx.face_proj_reals()), dtype=data.dtype,
+                                              device=data.device)
+
+    def halo_tensor(self):
+        """The per-cell array whose copy regions travel to the peers' ghost regions."""
+        return self.d.face_proj if self.faceproj else self.d.buffers
 
     def _rows(self, t, a, b):
         return self.api.strided(t[a:b])
 
     def local(self, a, b, stream=None):
-        """ader + volume + local flux for own cells [a, b): writes buffers[a:b] and dofs[a:b]."""
+        """ader + volume + local flux for own cells [a, b): writes buffers[a:b] (and face_proj[a:b]) and dofs[a:b]."""
         if b <= a:
             return
         d = self.d
         self.ctx.ader(self._rows(d.dofs, a, b), self._rows(d.buffers, a, b), None, self._rows(d.local_int, a, b),
                       self.coeffs, b - a, stream=stream)
-        self.ctx.local(self._rows(d.dofs, a, b), self._rows(d.buffers, a, b), self._rows(d.local_int, a, b),
-                       d.face_types[a:b], b - a, stream=stream)
+        if self.faceproj:
+            self.ctx.local_faceproj(self._rows(d.dofs, a, b), self._rows(d.buffers, a, b), self._rows(d.local_int, a, b),
+                                    self._rows(d.face_proj, a, b), d.face_types[a:b], b - a, stream=stream)
+        else:
+            self.ctx.local(self._rows(d.dofs, a, b), self._rows(d.buffers, a, b), self._rows(d.local_int, a, b),
+                           d.face_types[a:b], b - a, stream=stream)
 
     def neigh(self, stream=None):
-        """neighbor flux for all own cells; neighbors index the whole buffers array (own + ghost)."""
+        """neighbor flux for all own cells; neighbors index the whole per-cell array (own + ghost)."""
         d = self.d
+        if self.faceproj:
+            self.ctx.neigh_faceproj(self.api.strided(d.dofs), self.api.strided(d.face_proj), self.api.strided(d.neigh_int),
+                                    d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
+            return
         self.ctx.neigh(self.api.strided(d.dofs), self.api.strided(d.buffers), self.api.strided(d.neigh_int),
                        d.face_types, d.face_rel, d.cells, nb_idx=d.neighbors, perm=d.perm, stream=stream)
 

@@ -169,32 +169,61 @@ class LtsSolver:
 
 
 class CudaLtsBackend:
-    """predict / correct of one cluster through the C ABI (seissol_b200/api.py) on the re-ordered device arrays."""
+    """predict / correct of one cluster through the C ABI (seissol_b200/api.py) on the re-ordered device arrays.
 
-    def __init__(self, torch, ctx, plan, dofs, local_int, neigh_int, dist=None):
+    faceproj (default at order >= 6; SSB_FACEPROJ=0 switches it off): the neighbor flux runs on face projections
+    (include/seissol_b200.h): the local kernel stores F_f = fMrT_f I for the four faces of every own cell, cells that
+    accumulate for a larger cluster accumulate these blocks, neighbors that are read through their derivatives get
+    the Taylor sum AND the projection of the one face the reader sees in one kernel (ssb_taylor_faceproj), and the halo
+    carries the copy cells' projection blocks.  FaceNeighbors then points at projection blocks instead of time-integrated
+    DOFs; the schedule is unchanged."""
+
+    def __init__(self, torch, ctx, plan, dofs, local_int, neigh_int, dist=None, faceproj=None):
+        import os
         from . import api
         t = torch
         self.torch, self.api, self.ctx, self.plan = t, api, ctx, plan
         dev, dt = dofs.device, dofs.dtype
+        if faceproj is None:
+            faceproj = os.environ.get("SSB_FACEPROJ", "1" if ctx.order >= 6 else "0") != "0"
+        self.faceproj = bool(faceproj)
         self.dofs, self.local_int, self.neigh_int = dofs, local_int, neigh_int
         n, w = plan.n, dofs.shape[1]
-        self.idofs = t.zeros((n + plan.n_ghost, w), dtype=dt, device=dev)   # own cells, then the ghost layer
-        self.acc = t.zeros((max(plan.n_acc, 1), w), dtype=dt, device=dev)
+        es = dofs.element_size()
         self.derivs = t.zeros((max(plan.n_der, 1), ctx.dersize), dtype=dt, device=dev)
-        self.scratch = t.zeros((max(plan.n_scratch, 1), w), dtype=dt, device=dev)
         self.face_types = t.from_numpy(np.ascontiguousarray(plan.face_types)).to(dev)
         self.face_rel = t.from_numpy(np.ascontiguousarray(plan.face_rel)).to(dev)
-        es = dofs.element_size()
-        # LTS::FaceNeighbors: where the neighbor flux of (cell, face) reads the neighbor's time-integrated DOFs
-        # kind 0: a smaller-cluster neighbor's accumulation buffer, else the neighbor's own integral of this step
-        # (same cluster, local or ghost row); kind 1/2: the Taylor scratch row of this (cell, face)
         nb = plan.neighbors
         ghost = nb >= n
         nbl = np.where(ghost, 0, nb)
         smaller = ~ghost & (plan.cluster[nbl] == plan.cluster[:, None] - 1) & (plan.face_types == 0)
-        ptr = np.where(plan.kind > 0, self.scratch.data_ptr() + plan.scratch_row * w * es,
-                       np.where(smaller, self.acc.data_ptr() + plan.acc_row[nbl] * w * es,
-                                self.idofs.data_ptr() + nb * w * es))
+        if self.faceproj:
+            fp = ctx.face_proj_reals()
+            prj = fp // 4
+            self.fp, self.prj = fp, prj
+            self.idofs = t.zeros((n, w), dtype=dt, device=dev)                 # own cells only: no ghost I is needed
+            self.face_proj = t.zeros((n + plan.n_ghost, fp), dtype=dt, device=dev)
+            self.acc = t.zeros((max(plan.n_acc, 1), fp), dtype=dt, device=dev)
+            self.scratch = t.zeros((max(plan.n_scratch, 1), prj), dtype=dt, device=dev)
+            self.halo = self.face_proj
+            j = plan.face_rel[:, :, 0].astype(np.int64)
+            # LTS::FaceNeighbors for the projection path: the kernel adds j * prj reals to the entry
+            ptr = np.where(plan.kind > 0, self.scratch.data_ptr() + (plan.scratch_row * prj - j * prj) * es,
+                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nbl] * fp * es,
+                                    self.face_proj.data_ptr() + nb * fp * es))
+            scratch_width = prj
+        else:
+            self.idofs = t.zeros((n + plan.n_ghost, w), dtype=dt, device=dev)   # own cells, then the ghost layer
+            self.acc = t.zeros((max(plan.n_acc, 1), w), dtype=dt, device=dev)
+            self.scratch = t.zeros((max(plan.n_scratch, 1), w), dtype=dt, device=dev)
+            self.halo = self.idofs
+            # LTS::FaceNeighbors: where the neighbor flux of (cell, face) reads the neighbor's time-integrated DOFs
+            # kind 0: a smaller-cluster neighbor's accumulation buffer, else the neighbor's own integral of this step
+            # (same cluster, local or ghost row); kind 1/2: the Taylor scratch row of this (cell, face)
+            ptr = np.where(plan.kind > 0, self.scratch.data_ptr() + plan.scratch_row * w * es,
+                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nbl] * w * es,
+                                    self.idofs.data_ptr() + nb * w * es))
+            scratch_width = w
         self.nb_ptrs = t.from_numpy(np.ascontiguousarray(ptr.astype(np.int64))).to(dev)
         self.taylor = {}
         for name, store in (("full", plan.taylor_full), ("sub", plan.taylor_sub)):
@@ -202,9 +231,10 @@ class CudaLtsBackend:
                 if len(e) == 0:
                     continue
                 src = self.derivs.data_ptr() + plan.der_row[nb[e, f]] * ctx.dersize * es
-                dst = self.scratch.data_ptr() + plan.scratch_row[e, f] * w * es
+                dst = self.scratch.data_ptr() + plan.scratch_row[e, f] * scratch_width * es
+                face_j = t.from_numpy(np.ascontiguousarray(plan.face_rel[e, f, 0].astype(np.uint8))).to(dev)
                 self.taylor[(name, c)] = (t.from_numpy(src.astype(np.int64)).to(dev), t.from_numpy(dst.astype(np.int64)).to(dev),
-                                          len(e))
+                                          len(e), face_j)
         self.perm = {}
         for c, r in enumerate(plan.ranges):
             rel = plan.face_rel[r.start:r.end].astype(np.int64)
@@ -213,31 +243,33 @@ class CudaLtsBackend:
             self.perm[c] = t.from_numpy(np.argsort(key, kind="stable").astype(np.int32)).to(dev)
         self.launches = 0
         self.dist = dist
-        self.comm, self.pending = None, set()
-        self.send_idx = {c: [(peer, side, t.from_numpy(np.ascontiguousarray(idx)).to(dev)) for peer, side, idx in regs]
+        self.pending = set()
+        # halo: persistent pack buffers (one per cluster and region), communication stream and events created once
+        self.send_idx = {c: [(peer, side, t.from_numpy(np.ascontiguousarray(idx)).to(dev),
+                              t.empty((len(idx), self.halo.shape[1]), dtype=dt, device=dev)) for peer, side, idx in regs]
                          for c, regs in plan.send.items()}
-
-    def exchange(self, c):
-        """Halo of cluster c: pack the copy cells' time-integrated DOFs per region (index_select), one NCCL send/recv
-        pair per region, received straight into the ghost rows the neighbor kernel reads.  Runs on a communication
-        stream behind the prediction of cluster c; only the correction of cluster c waits for it, so the predictions
-        and corrections of the other clusters overlap the transfer."""
-        t, dist, plan = self.torch, self.dist, self.plan
-        if self.comm is None:
-            self.comm = t.cuda.Stream(self.idofs.device)
+        self.comm = None
+        if dist is not None and dofs.is_cuda and plan.world > 1:
+            self.comm = t.cuda.Stream(dev)
             self.ev_pred = {k: t.cuda.Event() for k in range(plan.n_clusters)}
             self.ev_halo = {k: t.cuda.Event() for k in range(plan.n_clusters)}
-        main = t.cuda.current_stream(self.idofs.device)
+
+    def exchange(self, c):
+        """Halo of cluster c: pack the copy cells' rows (time-integrated DOFs, or face projections) per region into a
+        persistent buffer, one NCCL send/recv pair per region, received straight into the ghost rows the neighbor kernel
+        reads.  Runs on a communication stream behind the prediction of cluster c; only the correction of cluster c
+        waits for it, so the predictions and corrections of the other clusters overlap the transfer."""
+        t, dist, plan = self.torch, self.dist, self.plan
+        main = t.cuda.current_stream(self.halo.device)
         self.ev_pred[c].record(main)
         with t.cuda.stream(self.comm):
             self.comm.wait_event(self.ev_pred[c])
-            ops, keep = [], []
-            for peer, side, idx in sorted(self.send_idx[c], key=lambda r: r[1]):
-                buf = self.idofs.index_select(0, idx)
-                keep.append(buf)
+            ops = []
+            for peer, side, idx, buf in sorted(self.send_idx[c], key=lambda r: r[1]):
+                t.index_select(self.halo, 0, idx, out=buf)
                 ops.append(dist.P2POp(dist.isend, buf, peer, tag=2 * c + side))
             for peer, side, start, count in sorted(plan.recv[c], key=lambda r: 1 - r[1]):
-                ops.append(dist.P2POp(dist.irecv, self.idofs[start:start + count], peer, tag=2 * c + (1 - side)))
+                ops.append(dist.P2POp(dist.irecv, self.halo[start:start + count], peer, tag=2 * c + (1 - side)))
             if ops:
                 for wk in dist.batch_isend_irecv(ops):
                     wk.wait()
@@ -259,28 +291,45 @@ class CudaLtsBackend:
             ctx.ader(self._s(self.dofs, r.der_end, r.end), self._s(self.idofs, r.der_end, r.end), None,
                      self._s(self.local_int, r.der_end, r.end), coeffs, r.end - r.der_end)
             self.launches += 1
-        ctx.local(self._s(self.dofs, r.start, r.end), self._s(self.idofs, r.start, r.end), self._s(self.local_int, r.start, r.end),
-                  self.face_types[r.start:r.end], r.end - r.start)
+        if self.faceproj:
+            ctx.local_faceproj(self._s(self.dofs, r.start, r.end), self._s(self.idofs, r.start, r.end),
+                               self._s(self.local_int, r.start, r.end), self._s(self.face_proj, r.start, r.end),
+                               self.face_types[r.start:r.end], r.end - r.start)
+        else:
+            ctx.local(self._s(self.dofs, r.start, r.end), self._s(self.idofs, r.start, r.end),
+                      self._s(self.local_int, r.start, r.end), self.face_types[r.start:r.end], r.end - r.start)
         self.launches += 1
         if r.acc_end > r.start:
             a0 = int(plan.acc_row[r.start])
-            ctx.lts_accumulate(self._s(self.acc, a0, a0 + r.acc_end - r.start), self._s(self.idofs, r.start, r.acc_end), reset,
-                               r.acc_end - r.start)
+            if self.faceproj:
+                ctx.accumulate_rows(self._s(self.acc, a0, a0 + r.acc_end - r.start), self._s(self.face_proj, r.start, r.acc_end),
+                                    reset, r.acc_end - r.start, self.fp)
+            else:
+                ctx.lts_accumulate(self._s(self.acc, a0, a0 + r.acc_end - r.start), self._s(self.idofs, r.start, r.acc_end),
+                                   reset, r.acc_end - r.start)
             self.launches += 1
 
     def correct(self, c, r, coeffs_full, coeffs_sub):
         ctx, api = self.ctx, self.api
         if c in self.pending:      # the ghost rows of this cluster must have arrived
-            self.torch.cuda.current_stream(self.idofs.device).wait_event(self.ev_halo[c])
+            self.torch.cuda.current_stream(self.halo.device).wait_event(self.ev_halo[c])
             self.pending.discard(c)
         for name, coeffs in (("full", coeffs_full), ("sub", coeffs_sub)):
             if (name, c) in self.taylor:
-                src, dst, cnt = self.taylor[(name, c)]
-                ctx.taylor(api.pointer_table(src), api.pointer_table(dst), coeffs, cnt)
+                src, dst, cnt, face_j = self.taylor[(name, c)]
+                if self.faceproj:
+                    ctx.taylor_faceproj(api.pointer_table(src), api.pointer_table(dst), face_j, coeffs, cnt)
+                else:
+                    ctx.taylor(api.pointer_table(src), api.pointer_table(dst), coeffs, cnt)
                 self.launches += 1
-        ctx.neigh(self._s(self.dofs, r.start, r.end), api.NONE, self._s(self.neigh_int, r.start, r.end),
-                  self.face_types[r.start:r.end], self.face_rel[r.start:r.end], r.end - r.start,
-                  nb_ptrs=self.nb_ptrs[r.start:r.end], perm=self.perm[c])
+        if self.faceproj:
+            ctx.neigh_faceproj(self._s(self.dofs, r.start, r.end), None, self._s(self.neigh_int, r.start, r.end),
+                               self.face_types[r.start:r.end], self.face_rel[r.start:r.end], r.end - r.start,
+                               nb_ptrs=self.nb_ptrs[r.start:r.end], perm=self.perm[c])
+        else:
+            ctx.neigh(self._s(self.dofs, r.start, r.end), api.NONE, self._s(self.neigh_int, r.start, r.end),
+                      self.face_types[r.start:r.end], self.face_rel[r.start:r.end], r.end - r.start,
+                      nb_ptrs=self.nb_ptrs[r.start:r.end], perm=self.perm[c])
         self.launches += 1
 
 

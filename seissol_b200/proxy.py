@@ -25,6 +25,8 @@ TIMESTEP = 1.0  # src/Proxy/Constants.h
 FLOPS = {
     4: {"derivative": (6642, 34146), "volume": (4806, 19584), "localFlux": (18972, None),
         "neighboringFlux": (4 * 5073.0, None)},
+    5: {"derivative": (20943, 98001), "volume": (13986, 56448), "localFlux": (40320, 102528),
+        "neighboringFlux": (4 * 10671.0, 4 * 29952)},
     6: {"derivative": (56286, 248292), "volume": (34839, 127872), "localFlux": (79200, 246528),
         "neighboringFlux": (4 * 20805.0, 4 * 73728)},
 }
@@ -161,7 +163,9 @@ class ProxyKernels:
         self.ctx, self.d = ctx, data
         self.coeffs = integrate_coeffs(ctx.order, 0.0, TIMESTEP)
         if faceproj is None:
-            faceproj = os.environ.get("SSB_FACEPROJ", "1") != "0"
+            # pays where the rT_j products dominate the neighbor kernel: order 6 (all 3.21 -> 3.82 ms at order 4, equal
+            # at order 5, 9.1 -> 8.2 ms at order 6; profiles/r2_quick_bench_orders.txt)
+            faceproj = os.environ.get("SSB_FACEPROJ", "1" if ctx.order >= 6 else "0") != "0"
         self.faceproj = bool(faceproj)
         if self.faceproj and getattr(data, "face_proj", None) is None:
             data.face_proj = data.torch.zeros((data.cells, ctx.face_proj_reals()), dtype=data.dtype, device=data.device)

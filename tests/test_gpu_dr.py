@@ -266,3 +266,151 @@ def test_fault_time_step_chain(gpu, order):
     assert rel_l2(got, want) < 1e-11
     assert rel_l2(got - q_loc, want - q_loc) < 1e-9            # the neighbor + nodal-flux update itself
     assert np.abs(d["slip_rate_magnitude"].cpu().numpy()[:, :P] - st_o["slipRateMagnitude"]).max() < 1e-9
+
+
+def _chain_problem(order, n, m, seed, law):
+    """Cells with m fault faces (distinct (cell, side) pairs for the plus and the minus side) among regular faces, in
+    physical units: stresses O(1e6) Pa in Q, fault pre-stress O(1e8) Pa; every flux matrix (AplusT, AminusT AND the
+    fault's fluxSolver) is scaled like the proxy's so that a step is a contraction and the fault faces contribute to the
+    update at the same magnitude as the regular faces."""
+    dt = np.float64
+    rng = np.random.default_rng(seed)
+    host = O.proxy_data(order, n, dt, seed=seed + 1)
+    host["Q"] = host["Q"] * 1e6
+    slots = rng.permutation(4 * n)[:2 * m]
+    plus_cell, plus_side = slots[:m] // 4, slots[:m] % 4
+    minus_cell, minus_side = slots[m:] // 4, slots[m:] % 4
+    rel = rng.integers(1, 4, m)
+    ft = np.zeros((n, 4), dtype=np.uint8)
+    ft[plus_cell, plus_side] = 3
+    ft[minus_cell, minus_side] = 3
+    host["face_types"] = ft
+    info = np.stack([plus_side, minus_side, rel], 1).astype(np.uint8)
+    q, _ = np.linalg.qr(rng.normal(size=(m, 9, 9)))           # rotation-like TinvT
+    tinv = q.astype(dt)
+    flux_solver = (rng.uniform(-1, 1, (2 * m, 9, 9)) * 1e-2).astype(dt)
+    st, imp, params = F.fault_state(law, m, order, dt, seed=seed + 2)
+    dr_index = np.zeros((n, 4), dtype=np.int64)
+    dr_side = np.zeros((n, 4), dtype=np.uint8)
+    dr_rel = np.zeros((n, 4), dtype=np.uint8)
+    dr_index[plus_cell, plus_side] = np.arange(m)
+    dr_side[plus_cell, plus_side] = plus_side
+    dr_index[minus_cell, minus_side] = m + np.arange(m)
+    dr_side[minus_cell, minus_side] = minus_side
+    dr_rel[minus_cell, minus_side] = rel
+    return dict(host=host, plus_cell=plus_cell, minus_cell=minus_cell, info=info, tinv=tinv, flux_solver=flux_solver,
+                st=st, imp=imp, params=params, dr_index=dr_index, dr_side=dr_side, dr_rel=dr_rel, ft=ft)
+
+
+def _round_inputs(pb, dt):
+    """The inputs as the device sees them in precision dt, promoted back to double for the oracle."""
+    r = lambda x: x.astype(dt).astype(np.float64) if x.dtype.kind == "f" else x  # noqa: E731
+    out = dict(pb)
+    out["host"] = {k: r(v) for k, v in pb["host"].items()}
+    out["tinv"], out["flux_solver"] = r(pb["tinv"]), r(pb["flux_solver"])
+    out["st"] = {k: r(v) for k, v in pb["st"].items()}
+    out["imp"] = {k: r(v) for k, v in pb["imp"].items()}
+    return out
+
+
+@pytest.mark.parametrize("law,order,dt,n,m", [("lsw", 6, np.float32, 8000, 10400), ("lsw", 6, np.float64, 1500, 2000),
+                                               ("rsfvw", 6, np.float64, 300, 320), ("rsfvw", 6, np.float32, 300, 320),
+                                               ("lsw", 4, np.float32, 1500, 2000)])
+def test_all_dr_friction_n_steps(gpu, law, order, dt, n, m):
+    """BASELINE.json's bar on the fault path: 10 time steps of the full chain on the device -- ader (+ derivatives) ->
+    local (fault faces skipped) -> godunov_dr -> friction law (state carried from step to step) -> neigh (regular faces)
+    + nodal flux of the imposed state -- against the same chain of oracle functions evaluated in DOUBLE precision on the
+    inputs rounded to the device precision: Q within 1e-5 (single) / 1e-11 (double); imposed state and the friction
+    state within the bounds documented below.  The first case has > 10 000 fault faces."""
+    torch, api, proxy = gpu
+    steps, step = 10, 1e-3
+    es = np.dtype(dt).itemsize
+    ctx = api.Context(order, es)
+    P = (order + 1) ** 2
+    pb = _round_inputs(_chain_problem(order, n, m, 101, law), dt)
+    tab = O.load_tables(order, np.float64)
+    host, st_o, imp = pb["host"], {k: v.copy() for k, v in pb["st"].items()}, pb["imp"]
+    plus_cell, minus_cell, info, ft = pb["plus_cell"], pb["minus_cell"], pb["info"], pb["ft"]
+    c_int = O.time_integrate_coeffs(order, 0.0, step, np.float64)
+    pts, _ = proxy.gauss_legendre_points(order, step)
+    c_pts = np.stack([proxy.point_coeffs(order, tau) for tau in pts]).astype(np.float64)
+    lawobj = (F.LinearSlipWeakening if law == "lsw" else F.RateAndStateFastVelocityWeakening)(pb["params"], tab["resample"])
+    star = O.star_dense(host["star"], tab["star_pattern"])
+    dr = {"fluxSolver": pb["flux_solver"], "index": pb["dr_index"], "side": pb["dr_side"], "rel": pb["dr_rel"]}
+
+    # ---- device set-up
+    dev = torch.device("cuda")
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    hd = {k: (v.astype(dt) if v.dtype.kind == "f" else v) for k, v in host.items()}
+    data = proxy.ProxyData.from_host(ctx, hd)
+    derivs = torch.zeros((n, ctx.dersize), device=dev, dtype=tdt)
+    stride = derivs.stride(0) * derivs.element_size()
+    pp = (derivs.data_ptr() + torch.from_numpy(plus_cell).to(dev) * stride).contiguous()
+    pm = (derivs.data_ptr() + torch.from_numpy(minus_cell).to(dev) * stride).contiguous()
+    qp = torch.zeros((m, order, 9, ctx.ppad), device=dev, dtype=tdt)
+    qm = torch.zeros_like(qp)
+    tinv_mem = torch.from_numpy(np.ascontiguousarray(pb["tinv"].transpose(0, 2, 1)).reshape(m, 81).astype(dt)).to(dev)
+    std = {k: (v.astype(dt) if v.dtype.kind == "f" else v) for k, v in pb["st"].items()}
+    impd = {k: v.astype(dt) for k, v in imp.items()}
+    d, names = _friction_device_data(torch, ctx, proxy, std, impd, np.zeros((m, order, P, 9), dtype=dt),
+                                     np.zeros((m, order, P, 9), dtype=dt), tab["resample"], law)
+    d["q_plus"], d["q_minus"] = qp, qm
+    imposed = torch.zeros((2 * m, 9, ctx.ppad), device=dev, dtype=tdt)     # plus faces, then minus faces
+    d["imposed_plus"], d["imposed_minus"] = imposed[:m], imposed[m:]
+    fs_mem = torch.from_numpy(np.ascontiguousarray(pb["flux_solver"].transpose(0, 2, 1)).reshape(2 * m, 81).astype(dt)).to(dev)
+    idx = torch.from_numpy(pb["dr_index"]).to(dev)
+    gp = (imposed.data_ptr() + idx * (9 * ctx.ppad * es)).contiguous()
+    fsp = (fs_mem.data_ptr() + idx * (81 * es)).contiguous()
+    sr = torch.from_numpy(np.stack([pb["dr_side"], pb["dr_rel"]], -1).astype(np.uint8)).to(dev).contiguous()
+    info_d = torch.from_numpy(info).to(dev)
+
+    Q = host["Q"]
+    dr_part = 0.0
+    for s in range(steps):
+        t_now = s * step
+        fp, dts, wts = proxy.friction_params(order, step, full_update_time=t_now, rs_sr0=pb["params"].rsSr0,
+                                             healing_threshold=pb["params"].healingThreshold, t0=pb["params"].t0)
+        # ---- oracle chain (double precision)
+        I, ders = O.ader(tab, Q, star, c_int, True)
+        q_loc = O.local(tab, Q, I, star, O.flux_dense(host["Aplus"]), ft)
+        qip, qim = O.dr_interpolate(tab, [x[plus_cell] for x in ders], [x[minus_cell] for x in ders], pb["tinv"], info, c_pts)
+        imp_plus, imp_minus = F.evaluate(lawobj, st_o, imp, qip, qim, t_now, dts, wts)
+        dr["godunov"] = np.concatenate([imp_plus, imp_minus])
+        q_reg = O.neighbor(tab, q_loc, I, host["neighbors"], O.flux_dense(host["Aminus"]), host["face_rel"], ft)
+        Q = O.neighbor(tab, q_loc, I, host["neighbors"], O.flux_dense(host["Aminus"]), host["face_rel"], ft, dr=dr)
+        dr_part = max(dr_part, np.linalg.norm(Q - q_reg) / np.linalg.norm(Q - q_loc))
+        # ---- device chain
+        ctx.ader(api.strided(data.dofs), api.strided(data.buffers), api.strided(derivs), api.strided(data.local_int), c_int, n)
+        ctx.local(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.local_int), data.face_types, n)
+        ctx.dr_interp(api.pointer_table(pp), api.pointer_table(pm), tinv_mem, info_d, qp, qm, c_pts, m)
+        ctx.friction(law, d, fp, m)
+        ctx.neigh(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.neigh_int), data.face_types, data.face_rel,
+                  n, nb_idx=data.neighbors)
+        ctx.neigh_dr(api.strided(data.dofs), gp, fsp, sr, data.face_types, n)
+    torch.cuda.synchronize()
+    # the fault contributes to the update at the magnitude of the regular faces (not hidden behind a tiny flux solver)
+    assert dr_part > 0.2, dr_part
+    got = data.to_logical(data.dofs).astype(np.float64)
+    err_q = rel_l2(got, Q)
+    got_p = proxy.points_from_device(ctx, imposed[:m].cpu().numpy(), P).astype(np.float64)
+    got_m = proxy.points_from_device(ctx, imposed[m:].cpu().numpy(), P).astype(np.float64)
+    err_imp = max(rel_l2(got_p, imp_plus), rel_l2(got_m, imp_minus))
+    # Bounds.  Linear slip weakening is piecewise smooth: double 1e-11, single 1e-5 like the DOFs.  Rate-and-state: the
+    # Newton iteration stops at |dV| < 1e-8 m/s (rsSlipRateTolerance, the reference's default), so two correct
+    # implementations agree in the slip rate to ~1e-8 absolute and in the tractions to ~1e-8 x eta_s ~ 0.05 Pa of 1e7..1e8 Pa:
+    # double 1e-8; in single precision the iterates cannot get below float resolution of the slip-rate scale either:
+    # 5e-5 on the imposed state, 1e-5 on the DOFs after the 1e-2-scaled flux solver.
+    if law == "lsw":
+        bar_q, bar_imp, bar_state = (1e-11, 1e-11, 1e-10) if dt == np.float64 else (1e-5, 1e-5, 2e-5)
+    else:
+        bar_q, bar_imp, bar_state = (1e-9, 1e-8, 1e-7) if dt == np.float64 else (1e-5, 5e-5, 2e-4)
+    assert np.isfinite(err_q) and err_q < bar_q, err_q
+    assert err_imp < bar_imp, err_imp
+    for k, v in names.items():
+        if k in ("d_c", "mu_s", "mu_d", "cohesion", "forced_rupture_time", "rs_a", "rs_sl0", "rs_f0", "rs_mu_w", "rs_b",
+                 "rs_sr_w", "rupture_time", "dyn_stress_time"):
+            continue
+        gotk = d[k].cpu().numpy()[:, :P].astype(np.float64)
+        want = st_o[v]
+        scale = max(np.linalg.norm(want), 1e-300)
+        assert np.linalg.norm(gotk - want) / scale < bar_state, (k, np.linalg.norm(gotk - want) / scale)

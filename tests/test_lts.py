@@ -118,7 +118,10 @@ def test_partitioned_lts_matches_single_rank(world, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("order,dt,bar", [(4, np.float32, 1e-5), (6, np.float32, 1e-5), (6, np.float64, 1e-11)])
-def test_lts_cuda_matches_brute_force(built_library, order, dt, bar):
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_lts_cuda_matches_brute_force(built_library, order, dt, bar, faceproj):
+    """faceproj: the LTS neighbor flux on face projections (accumulated projections for smaller-cluster neighbors,
+    ssb_taylor_faceproj for neighbors read through their derivatives)."""
     import torch
     from seissol_b200 import api
     ncl, dims = 3, (2, 2, 10)
@@ -131,7 +134,8 @@ def test_lts_cuda_matches_brute_force(built_library, order, dt, bar):
     qd = np.zeros((plan.n, 9, ctx.ld), dtype=dt)
     qd[:, :, :ctx.B] = Q.transpose(0, 2, 1)
     dofs = torch.from_numpy(qd.reshape(plan.n, 9 * ctx.ld)).to(dev)
-    be = L.CudaLtsBackend(torch, ctx, plan, dofs, torch.from_numpy(li).to(dev), torch.from_numpy(ni).to(dev))
+    be = L.CudaLtsBackend(torch, ctx, plan, dofs, torch.from_numpy(li).to(dev), torch.from_numpy(ni).to(dev),
+                          faceproj=faceproj)
     solver = L.LtsSolver(plan, be, order, dt0=0.5)
     want = Q
     for _ in range(2):
@@ -143,7 +147,7 @@ def test_lts_cuda_matches_brute_force(built_library, order, dt, bar):
     assert be.launches > 0
 
 
-def _cuda_lts_rank(rank, world, port, out):
+def _cuda_lts_rank(rank, world, port, out, faceproj=False):
     """One GPU per rank: partitioned LTS through the C ABI with NCCL; rank-local result saved for the comparison."""
     from seissol_b200 import api
     order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
@@ -161,7 +165,7 @@ def _cuda_lts_rank(rank, world, port, out):
     dofs = torch.from_numpy(qd.reshape(plan.n, 9 * ctx.ld)).to(dev)
     li = torch.from_numpy(M.element_values(plan.gid, 396, 1, 1e-2, dt)).to(dev)
     ni = torch.from_numpy(M.element_values(plan.gid, 324, 2, 1e-2, dt)).to(dev)
-    be = L.CudaLtsBackend(torch, ctx, plan, dofs, li, ni, dist=dist)
+    be = L.CudaLtsBackend(torch, ctx, plan, dofs, li, ni, dist=dist, faceproj=faceproj)
     solver = L.LtsSolver(plan, be, order, dt0=0.5)
     for _ in range(2):
         solver.macro_step()
@@ -174,13 +178,15 @@ def _cuda_lts_rank(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_partitioned_lts_cuda_two_gpus(built_library, tmp_path):
-    """2 GPUs, NCCL: the partitioned LTS run through the CUDA kernels matches the brute-force LTS of the whole mesh."""
+@pytest.mark.parametrize("faceproj", [False, True])
+def test_partitioned_lts_cuda_two_gpus(built_library, tmp_path, faceproj):
+    """2 GPUs, NCCL: the partitioned LTS run through the CUDA kernels matches the brute-force LTS of the whole mesh
+    (faceproj: the halo carries face projections)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
     out = str(tmp_path)
-    mp.spawn(_cuda_lts_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_cuda_lts_rank, args=(2, _free_port(), out, faceproj), nprocs=2, join=True)
     plan, Q, li, ni = make_problem(order, dt, dims, ncl)
     tab = O.load_tables(order, dt)
     star = O.star_dense(li[:, :72].reshape(-1, 3, 24), tab["star_pattern"])

@@ -115,6 +115,28 @@ f64v)
   SSB_FACEPROJ=0 SSB_KGEN5=0 timeout 300 python tools/quick_bench.py --order 4 --kernels ader,localwoader,neigh,all > $out/qb_o4_r1.txt 2>&1
   timeout 300 python tools/quick_bench.py --order 5 --kernels ader,localwoader,neigh,all > $out/qb_o5.txt 2>&1
   SSB_FACEPROJ=0 SSB_KGEN5=0 timeout 300 python tools/quick_bench.py --order 5 --kernels ader,localwoader,neigh,all > $out/qb_o5_r1.txt 2>&1 ;;
+ncuf64)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local' --launch-skip 4 -c 2 -f -o $out/full_f64fp \
+      python tools/quick_bench.py --real 8 --cells 148000 --steps 1 --kernels all > $out/ncu_f64fp.log 2>&1
+  SSB_FACEPROJ=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local' --launch-skip 4 -c 2 -f -o $out/full_f64nofp \
+      python tools/quick_bench.py --real 8 --cells 148000 --steps 1 --kernels all > $out/ncu_f64nofp.log 2>&1 ;;
+benchall)
+  timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "exit $?" >> $out/pytest.log
+  timeout 600 python bench.py > $out/bench_elastic_f32.json 2> $out/bench_elastic_f32.err
+  for c in elastic_f64 o4 visco dr_lsw dr_rsfvw; do
+    timeout 600 python bench.py --config $c --steps 10 > $out/bench_$c.json 2> $out/bench_$c.err
+  done
+  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref.json 2> $out/bench_ref.err ;;
+bench2)
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 5 --warmup 3 > $out/bench_lts2.json 2> $out/bench_lts2.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 10 --warmup 3 --lts 1 > $out/bench_gts2.json 2> $out/bench_gts2.err
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference > $out/bench_ref2.json 2> $out/bench_ref2.err
+  timeout 900 python -m pytest tests/test_lts.py -m gpu -x -q > $out/pytest_lts.log 2>&1; echo "exit $?" >> $out/pytest_lts.log ;;
+drtests)
+  timeout 1500 python -m pytest tests/test_gpu_dr.py tests/test_lts.py tests/test_gpu_parity.py tests/test_host_cpp.py -m gpu -x -q > $out/pytest_dr.log 2>&1; echo "exit $?" >> $out/pytest_dr.log
+  timeout 600 python bench.py --config dr_rsfvw --steps 10 > $out/bench_dr_rsfvw.json 2> $out/bench_dr_rsfvw.err
+  timeout 300 python tools/quick_bench_lts.py > $out/qb_lts.txt 2>&1
+  SSB_FACEPROJ=0 timeout 300 python tools/quick_bench_lts.py > $out/qb_lts_nofp.txt 2>&1 ;;
 ubench)
   timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
 qb)
