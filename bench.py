@@ -45,9 +45,9 @@ CONFIGS = {
                      baseline="configs[3], rate-and-state fast velocity weakening"),
 }
 LTS_CELLS_PER_GPU = 2_500_000
-# vector-FMA peak measured on this pool (tools/ubench/gen_ffma2.py, profiles/r2_ubench_fma_peak.txt): f32 = 148 SMs x 128
-# lanes x 2 flop x 1.965 GHz at the maximum clock, f64 at half rate
-FMA_PEAK_TFLOPS = {4: 74.2, 8: 37.1}
+# vector-FMA peak MEASURED on this pool (tools/ubench/fma_peak.cu -> profiles/r2_ubench_fma_peak.txt): FFMA 73.4 TFLOP/s
+# (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4), DFMA 34.3 TFLOP/s
+FMA_PEAK_TFLOPS = {4: 73.4, 8: 34.3}
 
 
 def measured_peaks():

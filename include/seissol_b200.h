@@ -166,7 +166,7 @@ typedef struct ssb_friction_data {
   const void* q_plus; const void* q_minus;            /* QInterpolatedPlus/Minus */
   void* imposed_plus; void* imposed_minus;            /* ImposedStatePlus/Minus [n][9][ppad] */
   const void* imp_and_eta;                            /* [n][11] ImpedancesAndEta (DynamicRupture/Typedefs.h:23-35) */
-  const void* initial_stress;                         /* InitialStressInFaultCS [n][6][ppad] */
+  const void* initial_stress;                         /* InitialStressInFaultCS [n][6][ppad]; written when nucleating */
   void* mu; void* slip1; void* slip2; void* slip_rate1; void* slip_rate2; void* slip_rate_magnitude;
   void* accumulated_slip_magnitude; void* traction1; void* traction2; void* rupture_time;
   void* peak_slip_rate; void* dyn_stress_time;
@@ -175,6 +175,14 @@ typedef struct ssb_friction_data {
   const void* rs_a; const void* rs_sl0; const void* rs_f0; const void* rs_mu_w; const void* rs_b; const void* rs_sr_w;
   void* state_variable; uint8_t* convergence_inner; uint8_t* convergence_outer;                      /* RS */
   const void* resample_t;                             /* [P][P], resample_t[j*P+p] = init::resample[p][j] */
+  /* nucleation + initial pressure (all optional, NULL = absent).  With nucleation_count > 0 in the parameters the kernel
+   * applies common::adjustInitialStress (FrictionSolverCommon.h:503-531) before every time point like
+   * BaseFrictionLaw::evaluate (CpuImpl/BaseFrictionLaw.h:106-118): initial_stress and initial_pressure are then UPDATED
+   * in place.  initial_pressure enters the normal stress of both laws (CpuImpl/LinearSlipWeakening.h:147-156,
+   * CpuImpl/RateAndState.h:418-433). */
+  void* initial_pressure;                             /* InitialPressure [n][ppad] */
+  const void* nucleation_stress;                      /* NucleationStressInFaultCS [n][nucleation_count][6][ppad] */
+  const void* nucleation_pressure;                    /* NucleationPressure [n][nucleation_count][ppad] */
 } ssb_friction_data_t;
 
 /* Scalars of FrictionSolver::evaluate and FrictionLawParameters (DynamicRupture/Misc.h:254-287). */
@@ -190,6 +198,10 @@ typedef struct ssb_friction_params {
   double rs_state_tolerance;
   int rs_max_number_slip_rate_updates;
   int rs_number_state_variable_updates;
+  int nucleation_count;    /* drParameters.nucleationCount (<= 4); 0 = no nucleation */
+  int reserved;
+  double nucleation_t0[4]; /* drParameters.t0[i]: effective rise time of nucleation i (t0[0] is also `t0` above) */
+  double nucleation_s0[4]; /* drParameters.s0[i]: onset time of nucleation i */
 } ssb_friction_params_t;
 
 /* FrictionSolver::evaluate (src/DynamicRupture/FrictionLaws/FrictionSolver.h:41) for

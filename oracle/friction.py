@@ -23,8 +23,10 @@ including its per-FACE convergence semantics (all points of a face iterate until
 Layout: per-face arrays are [nFaces, P] (P = (O+1)^2 points, no padding); QInterpolated is
 [nFaces, O, P, 9]; imposed states [nFaces, P, 9].  Quantity indices as
 DynamicRupture/Misc.h:217-234: N=0, T1=3, T2=5, U=6, V=7, W=8.
-Nucleation (adjustInitialStress) and thermal pressurisation are not part of the path
-(nucleationCount = 0, NoTP).
+Nucleation: adjustInitialStress (FrictionSolverCommon.h:503-531) per time point and the initial pressure in the normal
+stress (CpuImpl/LinearSlipWeakening.h:147-156, CpuImpl/RateAndState.h:418-433); smooth_step_increment is pinned by the
+closed form of the reference's own test (tests/Numerical/GaussianNucleation.t.h).  Thermal pressurisation is not part of
+the path (NoTP).
 """
 import math
 
@@ -58,6 +60,9 @@ class Params:
         self.t0 = 0.0
         self.etaDamp = 1.0
         self.etaDampEnd = math.inf
+        self.nucleationCount = 0
+        self.nucleationT0 = []
+        self.nucleationS0 = []
         self.rsMaxNumberSlipRateUpdates = 60
         self.rsNumberStateVariableUpdates = 10
         self.rsSlipRateTolerance = 1e-8
@@ -69,6 +74,32 @@ class Params:
 
 
 # ----------------------------------------------------------------------------- RateAndStateCommon.h
+def smooth_step(t, t0):
+    """gaussianNucleationFunction::smoothStep (src/Numerical/GaussianNucleationFunction.h:22-32), scalar of t's type."""
+    if t <= 0:
+        return type(t)(0)
+    if t < t0:
+        tau = t - t0
+        return type(t)(np.exp(tau * tau / (t * (t - type(t)(2) * t0))))
+    return type(t)(1)
+
+
+def smooth_step_increment(t, dt, t0):
+    """smoothStepIncrement (:37-40)."""
+    return smooth_step(t, t0) - smooth_step(t - dt, t0)
+
+
+def adjust_initial_stress(st, f, p, update_time, dt):
+    """common::adjustInitialStress (FrictionSolverCommon.h:503-531) for every nucleation of face f, in place on
+    st['initialStress'][f] ([6, P]) and st['initialPressure'][f]."""
+    for i in range(p.nucleationCount):
+        t0, s0 = update_time.__class__(p.nucleationT0[i]), update_time.__class__(p.nucleationS0[i])
+        if update_time <= t0 + s0 and update_time >= s0:
+            g = smooth_step_increment(update_time - s0, dt, t0)
+            st["initialStress"][f] += st["nucleationStress"][f, i] * g
+            st["initialPressure"][f] += st["nucleationPressure"][f, i] * g
+
+
 def almost_zero(dtype):
     return dtype(1e-45) if dtype == np.float64 else dtype(1e-35)
 
@@ -181,6 +212,8 @@ class LinearSlipWeakening:
         d_t = dt(dts[time_index])
         # calcStrengthHook (:141-163); initialPressure and fluidPressure are zero on this path
         total_normal = st["initialStress"][f, 0] + ns[time_index]
+        if "initialPressure" in st:      # + initialPressure (+ fluidPressure = 0 for elastic materials), :147-156
+            total_normal = total_normal + st["initialPressure"][f]
         strength = -st["cohesion"][f] - st["mu"][f] * np.minimum(total_normal, dt(0))
         # calcSlipRateAndTraction (:58-96)
         tt1 = st["initialStress"][f, 3] + t1[time_index]
@@ -272,7 +305,10 @@ class RateAndStateFastVelocityWeakening:
 
     def normal_stress(self, st, f, ns, time_index):
         """updateNormalStress (RateAndState.h:406-419), no fluid pressure."""
-        return np.minimum(ns.dtype.type(0), ns[time_index] + st["initialStress"][f, 0])
+        total = ns[time_index] + st["initialStress"][f, 0]
+        if "initialPressure" in st:      # RateAndState.h:418-433 (no thermal pressurisation)
+            total = total + st["initialPressure"][f]
+        return np.minimum(ns.dtype.type(0), total)
 
     def invert_slip_rate(self, st, imp, f, state, normal, shear):
         """invertSlipRateIterative (RateAndState.h:340-404): Newton on g(V); every point of the
@@ -371,6 +407,7 @@ def evaluate(law, st, imp, qip, qim, full_update_time, dts, time_weights):
         for ti in range(order):
             start_time = update_time
             update_time = dt(update_time + dt(dts[ti]))
+            adjust_initial_stress(st, f, law.p, update_time, dt(dts[ti]))     # BaseFrictionLaw.h:106-118
             law.update(st, imp, f, ns, t1, t2, tr1, tr2, state_buf, ti, dts, full_update_time)
             # saveRuptureFrontOutput (FrictionSolverCommon.h:546-566)
             hit = st["ruptureTimePending"][f] & (st["slipRateMagnitude"][f] > dt(0.001))

@@ -40,6 +40,14 @@ inline int ensureDynamicSmem(Kernel kern, size_t bytes, SmemConfig& cfg) {
   }
   return 0;
 }
+// Kernels that do not depend on a translation unit's generated operators (k_taylor<R>) are ONE function shared by all
+// configuration units: their shared-memory configuration must be one object too, otherwise a unit with a smaller
+// layout lowers the limit another unit relies on.  (inline template: one instance across translation units)
+template <typename Tag>
+inline SmemConfig& sharedSmemConfig() {
+  static SmemConfig cfg;
+  return cfg;
+}
 // SM count of the CURRENT device (cached per device ordinal)
 inline int smCountOfCurrentDevice() {
   static std::atomic<int> cache[64];

@@ -594,6 +594,17 @@ int friction(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params
   p.rsA = d->rs_a; p.rsSl0 = d->rs_sl0; p.rsF0 = d->rs_f0; p.rsMuW = d->rs_mu_w; p.rsB = d->rs_b; p.rsSrW = d->rs_sr_w;
   p.stateVariable = d->state_variable; p.convergenceInner = d->convergence_inner; p.convergenceOuter = d->convergence_outer;
   p.resampleT = d->resample_t;
+  p.initialPressure = d->initial_pressure;
+  p.nucleationStress = d->nucleation_stress;
+  p.nucleationPressure = d->nucleation_pressure;
+  p.nucleationCount = q->nucleation_count;
+  if (p.nucleationCount < 0 || p.nucleationCount > 4 || (p.nucleationCount > 0 && p.nucleationStress == nullptr)) {
+    return SSB_EINVAL;
+  }
+  for (int i = 0; i < 4; ++i) {
+    p.nucleationT0[i] = q->nucleation_t0[i];
+    p.nucleationS0[i] = q->nucleation_s0[i];
+  }
   const void* common[] = {p.qPlus, p.qMinus, p.imposedPlus, p.imposedMinus, p.impAndEta, p.initialStress, p.mu,
                           p.slip1, p.slip2, p.slipRate1, p.slipRate2, p.slipRateMagnitude, p.accumulatedSlipMagnitude,
                           p.traction1, p.traction2, p.ruptureTime, p.peakSlipRate, p.dynStressTime,

@@ -111,8 +111,8 @@ int taylorEntry(const TaylorParams& p, cudaStream_t stream) {
     return 0;
   }
   const size_t bytes = (size_t(kTaylorE) * (p.derSize + kNQ * p.ldg) * sizeof(Real) + 15) / 16 * 16 + 16;
-  static SmemConfig smemConfig;
-  if (int rc = ensureDynamicSmem(k_taylor<Real>, bytes, smemConfig)) {
+  // k_taylor<Real> is shared by every (order, generation) unit of this precision: one configuration object
+  if (int rc = ensureDynamicSmem(k_taylor<Real>, bytes, sharedSmemConfig<Real>())) {
     return rc;
   }
   k_taylor<Real><<<unsigned((p.n + kTaylorE - 1) / kTaylorE), 256, bytes, stream>>>(p);

@@ -2,6 +2,9 @@
 // The including file defines SSB_ORDER, SSB_REAL, SSB_TAG and includes gen/dr_o<SSB_ORDER>.cuh.
 #include "api_internal.h"
 #include "kernels_dr.cuh"
+#include "kernels_dr_tc.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
@@ -27,6 +30,12 @@ struct GenDr {
   }
   template <typename R>
   __device__ __forceinline__ static const R* nodalFluxTable() { return SSB_GEN_DR::nodalFluxTable<R>(); }
+  // tensor-core path: V3mTo2n as canonical tf32 hi / lo operands (gen_dr.py)
+  static constexpr int kTcK = SSB_GEN_DR::kTcK;
+  static constexpr int kTcN = SSB_GEN_DR::kTcN;
+  static constexpr int kTcOperand = SSB_GEN_DR::kTcOperand;
+  __device__ __forceinline__ static const float* v3CanonHi(int v) { return SSB_GEN_DR::v3CanonHi(v); }
+  __device__ __forceinline__ static const float* v3CanonLo(int v) { return SSB_GEN_DR::v3CanonLo(v); }
 };
 
 using Real = SSB_REAL;
@@ -38,9 +47,39 @@ int setSmem(K kern, size_t bytes, SmemConfig& configured) {
   return ensureDynamicSmem(kern, bytes, configured);
 }
 
+// single precision: the space-time interpolation runs on the tensor cores (k_dr_interp_tc: tcgen05 kind::tf32, 3-term
+// hi/lo split); SSB_DR_TC=0 selects the CUDA-core kernel (k_dr_interp) for A/B measurements
+inline bool useTensorCores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SSB_DR_TC");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && std::is_same<Real, float>::value;
+}
+
+int drInterpTcEntry(DrInterpParams& p, cudaStream_t stream) {
+  using C = DrTcCfg<GenO, GenDr>;
+  auto kern = k_dr_interp_tc<GenO, GenDr>;
+  p.rawStride = padOdd16(p.derSize, sizeof(float));
+  const size_t bytes = C::bytes(p.rawStride);
+  static SmemConfig configured;
+  if (int rc = setSmem(kern, bytes, configured)) {
+    return rc;
+  }
+  const long long tiles = (p.n + C::FPT - 1) / C::FPT;
+  const long long sms = smCountOfCurrentDevice();
+  const unsigned grid = unsigned(tiles < sms ? tiles : sms);
+  kern<<<grid, C::THREADS, bytes, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
 int drInterpEntry(DrInterpParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
+  }
+  if (useTensorCores()) {
+    return drInterpTcEntry(p, stream);
   }
   auto kern = k_dr_interp<Real, GenO, GenDr, NF>;
   p.rawStride = padOdd16(p.derSize, sizeof(Real));

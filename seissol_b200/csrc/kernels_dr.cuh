@@ -283,8 +283,26 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
       tr2[o] = R(0);
     }
   }
-  const R* stress = static_cast<const R*>(p.initialStress) + face * 6 * p.ppad + (active ? pt : 0);
-  const R s0 = stress[0], s3 = stress[3 * p.ppad], s5 = stress[5 * p.ppad];
+  // initial stress in fault coordinates; with nucleation it is ramped up in place, time point by time point
+  // (common::adjustInitialStress, FrictionSolverCommon.h:503-531, called from BaseFrictionLaw.h:106-118)
+  R* const stress = static_cast<R*>(const_cast<void*>(p.initialStress)) + face * 6 * p.ppad + (active ? pt : 0);
+  R s0 = stress[0], s3 = stress[3 * p.ppad], s5 = stress[5 * p.ppad];
+  const int nuc = p.nucleationCount;
+  R s1 = R(0), s2 = R(0), s4 = R(0);
+  if (nuc > 0) {
+    s1 = stress[1 * p.ppad]; s2 = stress[2 * p.ppad]; s4 = stress[4 * p.ppad];
+  }
+  R pressure = p.initialPressure != nullptr ? fp.template get<R>(p.initialPressure) : R(0);
+  auto smoothStep = [](R t, R t0) -> R {   // src/Numerical/GaussianNucleationFunction.h:22-32
+    if (t <= R(0)) {
+      return R(0);
+    }
+    if (t < t0) {
+      const R tau = t - t0;
+      return exp(tau * tau / (t * (t - R(2) * t0)));
+    }
+    return R(1);
+  };
 
   R mu = fp.template get<R>(p.mu);
   R slip1 = fp.template get<R>(p.slip1), slip2 = fp.template get<R>(p.slip2);
@@ -319,11 +337,23 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
     const R dt = static_cast<R>(p.deltaT[o]);
     const R startTime = updateTime;
     updateTime += dt;
+    for (int i = 0; i < nuc; ++i) {
+      const R nt0 = static_cast<R>(p.nucleationT0[i]), ns0 = static_cast<R>(p.nucleationS0[i]);
+      if (updateTime <= nt0 + ns0 && updateTime >= ns0) {
+        const R gNuc = smoothStep(updateTime - ns0, nt0) - smoothStep(updateTime - ns0 - dt, nt0);
+        const R* nst = static_cast<const R*>(p.nucleationStress) + (face * nuc + i) * 6 * p.ppad + (active ? pt : 0);
+        s0 += nst[0] * gNuc; s1 += nst[1 * p.ppad] * gNuc; s2 += nst[2 * p.ppad] * gNuc;
+        s3 += nst[3 * p.ppad] * gNuc; s4 += nst[4 * p.ppad] * gNuc; s5 += nst[5 * p.ppad] * gNuc;
+        if (p.nucleationPressure != nullptr) {
+          pressure += static_cast<const R*>(p.nucleationPressure)[(face * nuc + i) * p.ppad + (active ? pt : 0)] * gNuc;
+        }
+      }
+    }
     const R tt1 = s3 + t1[o];
     const R tt2 = s5 + t2[o];
     if constexpr (LAW == Law::LinearSlipWeakening) {
       // calcStrengthHook, calcSlipRateAndTraction (LinearSlipWeakening.h:141-163, 58-96)
-      const R strength = -cohesion - mu * min(s0 + ns[o], R(0));
+      const R strength = -cohesion - mu * min(s0 + ns[o] + pressure, R(0));   // + initialPressure, :147-156
       const R absT = hypot(tt1, tt2);
       srm = max(R(0), (absT - strength) * invEtaS);
       const R divisor = strength + etaS * srm;
@@ -363,7 +393,7 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
       // ---- RateAndStateBase::updateFrictionAndSlip (RateAndState.h:40-79)
       const R sr0 = static_cast<R>(p.rsSr0);
       const R stateRef = stateBuf;
-      const R normal = min(R(0), ns[o] + s0);  // updateNormalStress (:406-419), no fluid pressure
+      const R normal = min(R(0), ns[o] + s0 + pressure);  // updateNormalStress (:418-433), no thermal pressurisation
       const R shear = hypot(tt1, tt2);
       srm = max(rsAlmostZero<R>(), hypot(sr1, sr2));
       R localSr = srm;
@@ -484,6 +514,13 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
   for (int c = 0; c < 9; ++c) {
     ip[c * p.ppad] = valsP[c];
     im[c * p.ppad] = valsM[c];
+  }
+  if (nuc > 0) {
+    stress[0] = s0; stress[1 * p.ppad] = s1; stress[2 * p.ppad] = s2;
+    stress[3 * p.ppad] = s3; stress[4 * p.ppad] = s4; stress[5 * p.ppad] = s5;
+    if (p.initialPressure != nullptr) {
+      fp.template at<R>(p.initialPressure) = pressure;
+    }
   }
   fp.template at<R>(p.mu) = mu;
   fp.template at<R>(p.slip1) = slip1; fp.template at<R>(p.slip2) = slip2;

@@ -110,6 +110,13 @@ struct FrictionParams {
   double rsStateTolerance;
   int rsMaxNumberSlipRateUpdates;
   int rsNumberStateVariableUpdates;
+  // nucleation (common::adjustInitialStress) and initial pressure; initialStress is updated in place when nucleationCount > 0
+  void* initialPressure;            // [n][ppad] or null (= 0, not written)
+  const void* nucleationStress;     // [n][nucleationCount][6][ppad]
+  const void* nucleationPressure;   // [n][nucleationCount][ppad]
+  int nucleationCount;
+  double nucleationT0[4];
+  double nucleationS0[4];
 };
 
 struct NeighDrParams {

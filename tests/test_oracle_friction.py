@@ -120,3 +120,49 @@ def test_laws_run_and_respect_invariants(law_name, dt):
             # (and x*x + exp*exp underflows at the almostZero slip-rate floor: the reference formula itself)
             assert st["convergenceInner"].all() and st["convergenceOuter"].all()
             assert np.all(st["mu"] > 0) and np.all(st["mu"] < 1.5)
+
+
+def test_gaussian_nucleation_known_answers():
+    """The reference's own test of the nucleation function (tests/Numerical/GaussianNucleation.t.h:18-50): the increment of
+    the smooth step against the closed form, for rise times 0.8 and 1.0, dt = 0.01, i = -10..110, both precisions."""
+    for dt_ in (np.float32, np.float64):
+        step_w = dt_(0.01)
+        for rise in (dt_(0.8), dt_(1.0)):
+            def closed(t):
+                if t < 0:
+                    return dt_(0)
+                if t > rise:
+                    return dt_(1)
+                if t == 0:
+                    return dt_(0)
+                return dt_(np.exp((t - rise) * (t - rise) / (t * (t - 2 * rise))))
+            for i in range(-10, 111):
+                t = dt_(i) * step_w
+                got = F.smooth_step_increment(t, step_w, rise)
+                assert abs(got - (closed(t) - closed(t - step_w))) < 1e-4
+    # the increments of one rise sum to the full step
+    tot = sum(F.smooth_step_increment(np.float64(i * 0.01), np.float64(0.01), np.float64(0.8)) for i in range(0, 200))
+    assert abs(tot - 1.0) < 1e-12
+
+
+def test_adjust_initial_stress_ramps_to_the_nucleation_stress():
+    """common::adjustInitialStress (FrictionSolverCommon.h:503-531): over the rise time the initial stress gains exactly
+    the nucleation stress, the initial pressure the nucleation pressure (up to the last increment); outside [s0, s0 + t0] nothing changes."""
+    rng = np.random.default_rng(0)
+    P = 25
+    st = {"initialStress": np.zeros((1, 6, P)), "initialPressure": np.zeros((1, P)),
+          "nucleationStress": rng.uniform(-1, 1, (1, 2, 6, P)), "nucleationPressure": rng.uniform(-1, 1, (1, 2, P))}
+    p = F.Params()
+    p.nucleationCount, p.nucleationT0, p.nucleationS0 = 2, [0.4, 0.2], [0.0, 0.5]
+    dt = np.float64(0.005)
+    t = np.float64(0.0)
+    F.adjust_initial_stress(st, 0, p, np.float64(-1.0), dt)
+    assert np.all(st["initialStress"] == 0)
+    for _ in range(300):
+        t = t + dt
+        F.adjust_initial_stress(st, 0, p, t, dt)
+    # (the reference's window test `time <= t0 + s0` drops the last increment when the accumulated time lands a rounding
+    # error above the end of the rise: the sum misses at most that increment)
+    assert np.allclose(st["initialStress"][0], st["nucleationStress"][0].sum(0), atol=5e-3)
+    assert np.allclose(st["initialPressure"][0], st["nucleationPressure"][0].sum(0), atol=5e-3)
+    assert np.abs(st["initialStress"][0]).max() > 0.5
