@@ -5,6 +5,9 @@
 #include "kernels_elastic.cuh"
 #include "kernels_faceproj.cuh"
 #include "kernels_elastic5.cuh"
+#ifdef SSB_HAVE_TC
+#include "kernels_tc.cuh"
+#endif
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
@@ -142,10 +145,46 @@ int launchLocal(const LocalParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
+#ifdef SSB_HAVE_TC
+// Tensor-core predictor (kernels_tc.cuh), single precision: SSB_ADER_TC=1 (the CUDA-core kernel is the default).
+struct GenTc {
+  __device__ __forceinline__ static const float* aderOps() { return SSB_CAT(gen_tc_o, SSB_ORDER)::aderOps(); }
+};
+inline bool useAderTc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SSB_ADER_TC");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+int launchAderTc(const LocalParams& p, cudaStream_t stream) {
+  using C = tc::AderTc<Gen>;
+  auto kern = tc::k_ader_tc<Gen, GenTc>;
+  static SmemConfig smemConfig;
+  if (int rc = ensureDynamicSmem(kern, C::bytes, smemConfig)) {
+    return rc;
+  }
+  if (p.n <= 0) {
+    return 0;
+  }
+  const long long tiles = (p.n + tc::kTE - 1) / tc::kTE;
+  const long long ctas = (tiles + tc::kNW - 1) / tc::kNW;
+  const long long sms = smCount();
+  kern<<<unsigned(ctas < sms ? ctas : sms), tc::kNW * tc::kWT, C::bytes, stream>>>(p);
+  return int(cudaGetLastError());
+}
+#endif
+
 int localEntry(const LocalParams& p, bool ader, bool local, cudaStream_t stream) {
   if (ader && local) {
     return launchLocal<true, true>(p, stream);
   }
+#ifdef SSB_HAVE_TC
+  if (ader && useAderTc()) {
+    return launchAderTc(p, stream);
+  }
+#endif
 #if SSB_PACK_F32 == 1
   if (ader && (gen5Mask() & 2)) {
     return launchLocal5<true>(p, stream);

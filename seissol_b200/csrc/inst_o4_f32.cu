@@ -4,6 +4,8 @@
 #define SSB_MINB_LOCAL 4
 #define SSB_MINB_NEIGH 4
 #include "gen/ops_o4.cuh"
+#include "gen/tc_o4.cuh"
+#define SSB_HAVE_TC 1
 #define SSB_ORDER 4
 #define SSB_REAL float
 #define SSB_TAG o4_f32

@@ -4,6 +4,8 @@
 #define SSB_MINB_LOCAL 3
 #define SSB_MINB_NEIGH 3
 #include "gen/ops_o5.cuh"
+#include "gen/tc_o5.cuh"
+#define SSB_HAVE_TC 1
 #define SSB_ORDER 5
 #define SSB_REAL float
 #define SSB_TAG o5_f32

@@ -1,5 +1,7 @@
 // Kernel instantiation: elastic, order 6, float.
 #include "gen/ops_o6.cuh"
+#include "gen/tc_o6.cuh"
+#define SSB_HAVE_TC 1
 #define SSB_ORDER 6
 #define SSB_REAL float
 #define SSB_TAG o6_f32

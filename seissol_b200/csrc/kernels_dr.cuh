@@ -187,6 +187,20 @@ __device__ __forceinline__ bool rsBigBranch(R x, R expLog) {
   (void)frexp(x, &xexp);
   return expLog + R(max(xexp, 0)) * R(0.69314718055994530943) > R(10) || expLog >= R(50);
 }
+// sqrt(x^2 + e^2) of the big-argument branches.  Double precision: the reference's expression.  Single precision:
+// the same expression on operands scaled by 2^64 when both are tiny -- DELIBERATE DEVIATION from the reference's float arithmetic: with expLog = state / a ~ 60 the operands are
+// e ~ 1e-26 and x = cLin * slipRate, whose squares underflow in float as soon as a Newton iterate is clamped to
+// almostZero (1e-35); the reference's expression then returns log(x) instead of log(e): a NEGATIVE friction
+// coefficient and an infinite derivative, the iterate never leaves the clamp again and the point stays locked for the
+// rest of the run (found by the N-step parity run against the double-precision oracle, tests/test_gpu_dr.py).
+// Where nothing underflows the two agree to an ulp.
+__device__ __forceinline__ double rsHypot(double x, double e) { return sqrt(x * x + e * e); }
+__device__ __forceinline__ float rsHypot(float x, float e) {
+  const bool tiny = fabsf(x) < 1e-18f && fabsf(e) < 1e-18f;
+  const float up = tiny ? 18446744073709551616.f : 1.f, down = tiny ? 5.42101086242752217e-20f : 1.f;
+  const float xs = x * up, es = e * up;
+  return sqrtf(xs * xs + es * es) * down;
+}
 template <typename R>
 __device__ __forceinline__ R rsArsinhexp(R x, R expLog, R e) {
   if (rsBigBranch(x, expLog)) {
@@ -195,7 +209,7 @@ __device__ __forceinline__ R rsArsinhexp(R x, R expLog, R e) {
     }
     const R xa = fabs(x);
     const R xs = x >= R(0) ? R(1) : R(-1);
-    return xs * (expLog + log(xa + sqrt(xa * xa + e * e)));
+    return xs * (expLog + log(xa + rsHypot(xa, e)));
   }
   if (expLog > R(0)) {
     e = R(1) / e;
@@ -208,7 +222,7 @@ __device__ __forceinline__ R rsArsinhexpDerivative(R x, R expLog, R e) {
     if (expLog <= R(0)) {
       e = R(1) / e;
     }
-    return R(1) / sqrt(x * x + e * e);
+    return R(1) / rsHypot(x, e);
   }
   if (expLog > R(0)) {
     e = R(1) / e;

@@ -137,6 +137,14 @@ drtests)
   timeout 600 python bench.py --config dr_rsfvw --steps 10 > $out/bench_dr_rsfvw.json 2> $out/bench_dr_rsfvw.err
   timeout 300 python tools/quick_bench_lts.py > $out/qb_lts.txt 2>&1
   SSB_FACEPROJ=0 timeout 300 python tools/quick_bench_lts.py > $out/qb_lts_nofp.txt 2>&1 ;;
+tc)
+  SSB_ADER_TC=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ader" > $out/pytest_tc.log 2>&1; echo "exit $?" >> $out/pytest_tc.log
+  SSB_ADER_TC=1 timeout 300 python tools/quick_bench.py --kernels ader,all > $out/qb_tc.txt 2>&1
+  timeout 300 python tools/quick_bench.py --kernels ader,all > $out/qb_simt.txt 2>&1
+  SSB_ADER_TC=1 timeout 300 python tools/quick_bench.py --order 4 --kernels ader,all > $out/qb_tc_o4.txt 2>&1 ;;
+ncutc)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_ader_tc' --launch-skip 2 -c 1 -f -o $out/full_adertc \
+      env SSB_ADER_TC=1 python tools/quick_bench.py --cells 296000 --steps 1 --kernels ader > $out/ncu_adertc.log 2>&1 ;;
 umma)
   timeout 60 tools/ubench/umma_test > $out/umma_test.txt 2>&1; echo "exit $?" >> $out/umma_test.txt
   timeout 120 tools/ubench/fma_peak > $out/fma_peak.txt 2>&1 ;;
@@ -144,8 +152,8 @@ drtc)
   timeout 60 tools/ubench/umma_test > $out/umma_test.txt 2>&1; echo "exit $?" >> $out/umma_test.txt
   timeout 120 tools/ubench/fma_peak > $out/fma_peak.txt 2>&1
   timeout 900 python -m pytest tests/test_gpu_dr.py -m gpu -x -q -k "godunov or chain or n_steps" > $out/pytest_drtc.log 2>&1; echo "exit $?" >> $out/pytest_drtc.log
-  timeout 300 python tools/quick_bench_dr.py > $out/qbdr_tc.txt 2>&1
-  SSB_DR_TC=0 timeout 300 python tools/quick_bench_dr.py > $out/qbdr_simt.txt 2>&1
+  SSB_DR_TC=1 timeout 300 python tools/quick_bench_dr.py > $out/qbdr_tc.txt 2>&1
+  timeout 300 python tools/quick_bench_dr.py > $out/qbdr_simt.txt 2>&1
   timeout 900 python -m pytest tests/test_lts.py tests/test_gpu_parity.py tests/test_host_cpp.py tests/test_gpu_visco.py tests/test_planewave.py -m gpu -x -q > $out/pytest_rest.log 2>&1; echo "exit $?" >> $out/pytest_rest.log ;;
 ubench)
   timeout 300 tools/ubench/ifetch3 > $out/ifetch3.txt 2>&1 ;;
