@@ -47,14 +47,14 @@ int setSmem(K kern, size_t bytes, SmemConfig& configured) {
   return ensureDynamicSmem(kern, bytes, configured);
 }
 
-// single precision: SSB_DR_TC=1 runs the space-time interpolation on the tensor cores (k_dr_interp_tc: tcgen05
-// kind::tf32, 3-term hi/lo split); the CUDA-core kernel (k_dr_interp) is the default until the tensor-core kernel is
-// the faster one (profiles/: 5.30 vs 4.99 ms at 200 k faces)
+// single precision, order >= 5: the space-time interpolation runs on the tensor cores (k_dr_interp_tc: tcgen05 kind::tf32,
+// 3-term hi/lo split, A operand in tensor memory): 2.8 vs 5.0 ms at 200 k faces of order 6 (profiles/r2_dr_tc.txt); at
+// order 4 the CUDA-core kernel is as fast (1.11 vs 1.17 ms) and stays.  SSB_DR_TC=0 / 1 forces one or the other.
 inline bool useTensorCores() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("SSB_DR_TC");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = e == nullptr ? (SSB_ORDER >= 5 ? 1 : 0) : (e[0] == '1' ? 1 : 0);
   }
   return v == 1 && std::is_same<Real, float>::value;
 }
@@ -64,13 +64,17 @@ int drInterpTcEntry(DrInterpParams& p, cudaStream_t stream) {
   auto kern = k_dr_interp_tc<GenO, GenDr>;
   p.rawStride = padOdd16(p.derSize, sizeof(float));
   const size_t bytes = C::bytes(p.rawStride);
+  if (bytes > 227 * 1024) {
+    return -1;   // (padded reference layout of the derivative families at order 6): the caller takes the CUDA-core kernel
+  }
   static SmemConfig configured;
   if (int rc = setSmem(kern, bytes, configured)) {
     return rc;
   }
   const long long tiles = (p.n + C::FPT - 1) / C::FPT;
+  const long long ctas = (tiles + C::NW - 1) / C::NW;
   const long long sms = smCountOfCurrentDevice();
-  const unsigned grid = unsigned(tiles < sms ? tiles : sms);
+  const unsigned grid = unsigned(ctas < sms ? ctas : sms);
   kern<<<grid, C::THREADS, bytes, stream>>>(p);
   return int(cudaGetLastError());
 }
@@ -80,7 +84,10 @@ int drInterpEntry(DrInterpParams& p, cudaStream_t stream) {
     return 0;
   }
   if (useTensorCores()) {
-    return drInterpTcEntry(p, stream);
+    const int rc = drInterpTcEntry(p, stream);
+    if (rc != -1) {
+      return rc;
+    }
   }
   auto kern = k_dr_interp<Real, GenO, GenDr, NF>;
   p.rawStride = padOdd16(p.derSize, sizeof(Real));

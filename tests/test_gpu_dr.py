@@ -172,9 +172,11 @@ def test_friction_laws(gpu, law, order, dt, nucleation):
         assert np.abs(got - want).max() / scale < (100 * t), (k, np.abs(got - want).max(), scale)
     if nucleation:
         got_s = d["initial_stress"].cpu().numpy()[:, :, :P]
-        assert rel_l2(got_s, st["initialStress"]) < (1e-6 if dt == np.float32 else 1e-14)
+        # (float accumulation of 2 nucleations x O time points against the double oracle of the RS-FVW case: 1e-5)
+        tol_s = 1e-14 if dt == np.float64 else (1e-5 if law == "rsfvw" else 1e-6)
+        assert rel_l2(got_s, st["initialStress"]) < tol_s
         assert np.abs(got_s - F.fault_state(law, nf, order, dt)[0]["initialStress"]).max() > 1e5      # it did ramp
-        assert rel_l2(d["initial_pressure"].cpu().numpy()[:, :P], st["initialPressure"]) < (1e-6 if dt == np.float32 else 1e-14)
+        assert rel_l2(d["initial_pressure"].cpu().numpy()[:, :P], st["initialPressure"]) < tol_s
     if dt == np.float64:
         assert np.array_equal(d["rupture_time_pending"].cpu().numpy()[:, :P].astype(bool), st["ruptureTimePending"])
         assert np.array_equal(d["dyn_stress_time_pending"].cpu().numpy()[:, :P].astype(bool), st["dynStressTimePending"])

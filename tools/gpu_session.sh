@@ -145,6 +145,11 @@ tc)
 ncutc)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_ader_tc' --launch-skip 2 -c 1 -f -o $out/full_adertc \
       env SSB_ADER_TC=1 python tools/quick_bench.py --cells 296000 --steps 1 --kernels ader > $out/ncu_adertc.log 2>&1 ;;
+drtc2)
+  SSB_DR_TC=1 timeout 600 python -m pytest tests/test_gpu_dr.py -m gpu -q -k "godunov or chain or n_steps" > $out/pytest_drtc.log 2>&1; echo "exit $?" >> $out/pytest_drtc.log
+  SSB_DR_TC=1 timeout 300 python tools/quick_bench_dr.py > $out/qbdr_tc.txt 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp_tc' --launch-skip 2 -c 1 -f -o $out/full_drtc \
+      env SSB_DR_TC=1 python tools/quick_bench_dr.py --steps 1 > $out/ncu_drtc.log 2>&1 ;;
 umma)
   timeout 60 tools/ubench/umma_test > $out/umma_test.txt 2>&1; echo "exit $?" >> $out/umma_test.txt
   timeout 120 tools/ubench/fma_peak > $out/fma_peak.txt 2>&1 ;;
