@@ -65,6 +65,18 @@ class LtsPlan:
     rank: int = 0
     send: dict = field(default_factory=dict)   # cluster -> list of (peer, side, own cell indices in the peer's ghost order)
     recv: dict = field(default_factory=dict)   # cluster -> list of (peer, side, first ghost row, count)
+    # remote neighbors in ANOTHER time cluster (the copy regions of the reference carry "buffers and / or derivatives",
+    # InitProcedure/Internal/LtsSetup.cpp:115-189, DirectGhostTimeCluster.cpp:22-105):
+    #  * a ghost cell with an own neighbor in the next SMALLER cluster sends its derivative family after every
+    #    prediction; it lands in derivative rows behind the own ones (der_row is defined for ghost indices too);
+    #  * a ghost cell with an own neighbor in the next LARGER cluster is read through the sum of its two steps: the
+    #    RECEIVER accumulates the per-step rows it gets (acc_row is defined for ghost indices too).
+    cluster_ext: np.ndarray = None             # [n + n_ghost]
+    send_der: dict = field(default_factory=dict)    # cluster -> list of (peer, side, derivative rows to send)
+    recv_der: dict = field(default_factory=dict)    # cluster -> list of (peer, side, first derivative row, count)
+    ghost_acc: dict = field(default_factory=dict)   # cluster -> (ghost cell indices, accumulation rows)
+    n_der_own: int = 0
+    n_acc_own: int = 0
 
     def updates_per_macro_step(self):
         """Element updates in one step of the largest cluster."""
@@ -73,9 +85,9 @@ class LtsPlan:
 
 def build_plan(layout, n_clusters):
     """LtsPlan from a RankLayout (seissol_b200/partition.py::build_layout).  With more than one rank the ghost cells keep
-    their layout order behind the re-ordered own cells; the slab partition cuts along x and the time clusters are bands
-    in z, so a remote neighbor is always in the SAME cluster and the halo carries one time-integrated tensor per copy
-    cell and step of its cluster (checked here)."""
+    their layout order behind the re-ordered own cells.  The halo carries one time-integrated tensor per copy cell and
+    step of its cluster; where a slab boundary separates cells of different clusters it also carries the derivative
+    families of the larger cluster's copy cells, and the smaller cluster's ghost rows are accumulated on arrival."""
     n, ng = layout.n_own, layout.n_ghost
     cl_all = layout.cluster.astype(np.int64)
     cl = cl_all[:n]
@@ -86,8 +98,6 @@ def build_plan(layout, n_clusters):
     diff = np.where(regular, nb_cl - cl[:, None], 0)
     if np.abs(diff).max(initial=0) > 1:
         raise ValueError("neighboring cells may differ by at most one time cluster")
-    if np.any(diff[remote] != 0):
-        raise ValueError("remote neighbors must be in the same time cluster (x-slab partition, z-band clusters)")
     larger, smaller = diff == 1, diff == -1
     accumulates = larger.any(1)
     has_derivs = accumulates | smaller.any(1)
@@ -109,11 +119,22 @@ def build_plan(layout, n_clusters):
         g = group_o[a:b]
         ranges.append(ClusterRange(a, a + int((g == 0).sum()), a + int((g <= 1).sum()), b))
     acc_o, der_o = group_o == 0, group_o <= 1
-    der_row = np.where(der_o, np.cumsum(der_o) - 1, -1)
-    acc_row = np.where(acc_o, np.cumsum(acc_o) - 1, -1)
+    n_der_own, n_acc_own = int(der_o.sum()), int(acc_o.sum())
     cl_ext = np.concatenate([cl_o, cl_all[n:]])
-    acc_ext = np.concatenate([acc_o, np.zeros(ng, dtype=bool)])     # ghost cells are read through their per-step integral
     nb_cl = cl_ext[neighbors]
+    # ghost cells seen from a smaller / larger own cluster (layout order of the ghost cells = order of the messages)
+    ghost_der = np.zeros(ng, dtype=bool)
+    ghost_accm = np.zeros(ng, dtype=bool)
+    rem = regular & ~local_nb
+    e, f = np.nonzero(rem & (nb_cl == cl_o[:, None] + 1))
+    ghost_der[neighbors[e, f] - n] = True
+    e, f = np.nonzero(rem & (nb_cl == cl_o[:, None] - 1))
+    ghost_accm[neighbors[e, f] - n] = True
+    der_row = np.concatenate([np.where(der_o, np.cumsum(der_o) - 1, -1),
+                              np.where(ghost_der, n_der_own + np.cumsum(ghost_der) - 1, -1)])
+    acc_row = np.concatenate([np.where(acc_o, np.cumsum(acc_o) - 1, -1),
+                              np.where(ghost_accm, n_acc_own + np.cumsum(ghost_accm) - 1, -1)])
+    acc_ext = np.concatenate([acc_o, np.zeros(ng, dtype=bool)])     # same-cluster ghost cells: their per-step integral
     kind = np.zeros((n, 4), dtype=np.int64)
     kind[regular & local_nb & (nb_cl == cl_o[:, None]) & acc_ext[neighbors]] = 1
     kind[regular & (nb_cl == cl_o[:, None] + 1)] = 2
@@ -124,8 +145,12 @@ def build_plan(layout, n_clusters):
     assert np.all(acc_row[neighbors[sm]] >= 0)
     plan = LtsPlan(n=n, n_clusters=n_clusters, gid=layout.gid[:n][order], cluster=cl_o, neighbors=neighbors,
                    face_rel=layout.face_rel[order], face_types=face_types, ranges=ranges, der_row=der_row, acc_row=acc_row,
-                   kind=kind, scratch_row=scratch_row, n_der=int(der_o.sum()), n_acc=int(acc_o.sum()),
-                   n_scratch=int(need.sum()), n_ghost=ng, world=layout.world, rank=layout.rank)
+                   kind=kind, scratch_row=scratch_row, n_der=n_der_own + int(ghost_der.sum()),
+                   n_acc=n_acc_own + int(ghost_accm.sum()), n_scratch=int(need.sum()), n_ghost=ng, world=layout.world,
+                   rank=layout.rank, cluster_ext=cl_ext, n_der_own=n_der_own, n_acc_own=n_acc_own)
+    # own copy cells whose derivative family a peer needs: those with a remote neighbor in the next smaller cluster
+    # (an x-slab copy cell touches ONE peer region, so "any remote neighbor" and "a neighbor on that peer" coincide)
+    sends_der = (rem & (nb_cl == cl_o[:, None] - 1)).any(1)
     for c, r in enumerate(ranges):
         for k, store in ((1, plan.taylor_full), (2, plan.taylor_sub)):
             e, f = np.nonzero(kind[r.start:r.end] == k)
@@ -133,6 +158,20 @@ def build_plan(layout, n_clusters):
         plan.send[c] = [(reg.peer, reg.side, new_index[reg.start:reg.start + reg.count]) for reg in layout.send
                         if reg.cluster == c]
         plan.recv[c] = [(reg.peer, reg.side, reg.start, reg.count) for reg in layout.recv if reg.cluster == c]
+        plan.send_der[c], plan.recv_der[c] = [], []
+        for peer, side, idx in plan.send[c]:
+            sub = idx[sends_der[idx]]
+            if len(sub):
+                assert np.all(der_row[sub] >= 0)
+                plan.send_der[c].append((peer, side, der_row[sub]))
+        for peer, side, start, count in plan.recv[c]:
+            rows = der_row[start:start + count]
+            rows = rows[rows >= 0]
+            if len(rows):
+                assert np.array_equal(rows, np.arange(rows[0], rows[0] + len(rows)))
+                plan.recv_der[c].append((peer, side, int(rows[0]), len(rows)))
+        g = np.nonzero(ghost_accm & (cl_all[n:] == c))[0] + n
+        plan.ghost_acc[c] = (g, acc_row[g])
     return plan
 
 
@@ -155,11 +194,15 @@ class LtsSolver:
         plan, be = self.plan, self.be
         for s in range(self.fine_steps):
             for c, r in enumerate(plan.ranges):
-                if s % (2 ** c) == 0 and r.end > r.start:
-                    dt = self.dt0 * 2 ** c
-                    be.predict(c, r, integrate_coeffs(self.order, 0.0, dt), reset=(s % (2 ** (c + 1)) == 0))
-                    if plan.world > 1:
-                        be.exchange(c)      # copy cells of cluster c -> the peers' ghost rows (one message per region)
+                if s % (2 ** c) == 0:
+                    if r.end > r.start:
+                        dt = self.dt0 * 2 ** c
+                        be.predict(c, r, integrate_coeffs(self.order, 0.0, dt), reset=(s % (2 ** (c + 1)) == 0))
+                    if plan.world > 1 and (plan.send[c] or plan.recv[c]):
+                        # copy cells of cluster c -> the peers' ghost rows (one message per region; derivative
+                        # families where a peer integrates them); ghost rows read by a larger cluster are accumulated.
+                        # A rank without own cells of cluster c may still hold ghost cells of it.
+                        be.exchange(c, reset=(s % (2 ** (c + 1)) == 0))
             for c, r in enumerate(plan.ranges):
                 if (s + 1) % (2 ** c) == 0 and r.end > r.start:
                     dt = self.dt0 * 2 ** c
@@ -194,9 +237,9 @@ class CudaLtsBackend:
         self.face_types = t.from_numpy(np.ascontiguousarray(plan.face_types)).to(dev)
         self.face_rel = t.from_numpy(np.ascontiguousarray(plan.face_rel)).to(dev)
         nb = plan.neighbors
-        ghost = nb >= n
-        nbl = np.where(ghost, 0, nb)
-        smaller = ~ghost & (plan.cluster[nbl] == plan.cluster[:, None] - 1) & (plan.face_types == 0)
+        cl_ext = plan.cluster_ext if plan.cluster_ext is not None else plan.cluster
+        # neighbors (own or ghost cells) in the next smaller cluster: read through their accumulation row
+        smaller = (cl_ext[nb] == plan.cluster[:, None] - 1) & (plan.face_types == 0)
         if self.faceproj:
             fp = ctx.face_proj_reals()
             prj = fp // 4
@@ -209,7 +252,7 @@ class CudaLtsBackend:
             j = plan.face_rel[:, :, 0].astype(np.int64)
             # LTS::FaceNeighbors for the projection path: the kernel adds j * prj reals to the entry
             ptr = np.where(plan.kind > 0, self.scratch.data_ptr() + (plan.scratch_row * prj - j * prj) * es,
-                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nbl] * fp * es,
+                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nb] * fp * es,
                                     self.face_proj.data_ptr() + nb * fp * es))
             scratch_width = prj
         else:
@@ -221,7 +264,7 @@ class CudaLtsBackend:
             # kind 0: a smaller-cluster neighbor's accumulation buffer, else the neighbor's own integral of this step
             # (same cluster, local or ghost row); kind 1/2: the Taylor scratch row of this (cell, face)
             ptr = np.where(plan.kind > 0, self.scratch.data_ptr() + plan.scratch_row * w * es,
-                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nbl] * w * es,
+                           np.where(smaller, self.acc.data_ptr() + plan.acc_row[nb] * w * es,
                                     self.idofs.data_ptr() + nb * w * es))
             scratch_width = w
         self.nb_ptrs = t.from_numpy(np.ascontiguousarray(ptr.astype(np.int64))).to(dev)
@@ -248,17 +291,31 @@ class CudaLtsBackend:
         self.send_idx = {c: [(peer, side, t.from_numpy(np.ascontiguousarray(idx)).to(dev),
                               t.empty((len(idx), self.halo.shape[1]), dtype=dt, device=dev)) for peer, side, idx in regs]
                          for c, regs in plan.send.items()}
+        # ... derivative families of the copy cells a peer integrates in time, and the ghost rows a larger own cluster reads
+        # as a sum over two steps (accumulated on arrival)
+        self.send_der = {c: [(peer, side, t.from_numpy(np.ascontiguousarray(rows)).to(dev),
+                              t.empty((len(rows), ctx.dersize), dtype=dt, device=dev)) for peer, side, rows in regs]
+                         for c, regs in plan.send_der.items()}
+        self.ghost_acc = {}
+        for c, (g, rows) in plan.ghost_acc.items():
+            if len(g):
+                assert np.array_equal(rows, np.arange(rows[0], rows[0] + len(rows)))
+                src = self.halo.data_ptr() + g * self.halo.shape[1] * es
+                self.ghost_acc[c] = (t.from_numpy(src.astype(np.int64)).to(dev), int(rows[0]), len(g))
         self.comm = None
         if dist is not None and dofs.is_cuda and plan.world > 1:
             self.comm = t.cuda.Stream(dev)
             self.ev_pred = {k: t.cuda.Event() for k in range(plan.n_clusters)}
             self.ev_halo = {k: t.cuda.Event() for k in range(plan.n_clusters)}
 
-    def exchange(self, c):
+    def exchange(self, c, reset=True):
         """Halo of cluster c: pack the copy cells' rows (time-integrated DOFs, or face projections) per region into a
         persistent buffer, one NCCL send/recv pair per region, received straight into the ghost rows the neighbor kernel
-        reads.  Runs on a communication stream behind the prediction of cluster c; only the correction of cluster c
-        waits for it, so the predictions and corrections of the other clusters overlap the transfer."""
+        reads.  Where a slab boundary separates two clusters the copy cells of the larger one also send their derivative
+        families (received straight into derivative rows behind the own ones), and the ghost rows of the smaller one are
+        accumulated over its two steps on arrival (DirectGhostTimeCluster.cpp:22-105).  Runs on a communication stream
+        behind the prediction of cluster c; only the corrections that read these rows wait for it, so the other
+        predictions and corrections overlap the transfer."""
         t, dist, plan = self.torch, self.dist, self.plan
         main = t.cuda.current_stream(self.halo.device)
         self.ev_pred[c].record(main)
@@ -268,11 +325,23 @@ class CudaLtsBackend:
             for peer, side, idx, buf in sorted(self.send_idx[c], key=lambda r: r[1]):
                 t.index_select(self.halo, 0, idx, out=buf)
                 ops.append(dist.P2POp(dist.isend, buf, peer, tag=2 * c + side))
+            for peer, side, rows, buf in sorted(self.send_der.get(c, []), key=lambda r: r[1]):
+                t.index_select(self.derivs, 0, rows, out=buf)
+                ops.append(dist.P2POp(dist.isend, buf, peer, tag=64 + 2 * c + side))
             for peer, side, start, count in sorted(plan.recv[c], key=lambda r: 1 - r[1]):
                 ops.append(dist.P2POp(dist.irecv, self.halo[start:start + count], peer, tag=2 * c + (1 - side)))
+            for peer, side, row0, count in sorted(plan.recv_der.get(c, []), key=lambda r: 1 - r[1]):
+                ops.append(dist.P2POp(dist.irecv, self.derivs[row0:row0 + count], peer, tag=64 + 2 * c + (1 - side)))
             if ops:
                 for wk in dist.batch_isend_irecv(ops):
                     wk.wait()
+            if c in self.ghost_acc:
+                src, a0, cnt = self.ghost_acc[c]
+                if self.faceproj:
+                    self.ctx.accumulate_rows(self._s(self.acc, a0, a0 + cnt), self.api.pointer_table(src), reset, cnt, self.fp)
+                else:
+                    self.ctx.lts_accumulate(self._s(self.acc, a0, a0 + cnt), self.api.pointer_table(src), reset, cnt)
+                self.launches += 1
             self.ev_halo[c].record(self.comm)
         self.pending.add(c)
 
@@ -311,9 +380,11 @@ class CudaLtsBackend:
 
     def correct(self, c, r, coeffs_full, coeffs_sub):
         ctx, api = self.ctx, self.api
-        if c in self.pending:      # the ghost rows of this cluster must have arrived
-            self.torch.cuda.current_stream(self.halo.device).wait_event(self.ev_halo[c])
-            self.pending.discard(c)
+        for k in (c - 1, c, c + 1):   # the ghost rows this correction reads (own cluster, accumulated smaller, derivatives)
+            if k in self.pending:
+                self.torch.cuda.current_stream(self.halo.device).wait_event(self.ev_halo[k])
+                if k == c:
+                    self.pending.discard(k)
         for name, coeffs in (("full", coeffs_full), ("sub", coeffs_sub)):
             if (name, c) in self.taylor:
                 src, dst, cnt, face_j = self.taylor[(name, c)]

@@ -62,8 +62,23 @@ def cluster_of_z(cube_z, nz, n_clusters):
     return np.searchsorted(edges, depth, side="right").astype(np.int64)
 
 
-def build_layout(nx, ny, nz, rank, world, n_clusters=1):
-    """Layout of `rank`: which cells it owns, in which order, where its ghost cells sit and what is exchanged."""
+def cluster_of_x(cube_x, nx, n_clusters):
+    """Clusters varying ALONG the partition direction (periodic in x): two-cube layers that walk 0, 1, .., C-1, .., 1, 0, ..
+    so that EVERY even x is a cluster boundary.  Slab boundaries then separate cells of different time clusters: the halo
+    has to carry derivative families and the receiver has to accumulate ghost buffers (the general exchange of
+    seissol_b200/lts.py; nx must be a multiple of 4 (C - 1))."""
+    if n_clusters <= 1:
+        return np.zeros_like(cube_x)
+    period = 2 * (n_clusters - 1)
+    if nx % (2 * period):
+        raise ValueError("nx must be a multiple of 4 (clusters - 1) for clusters along x")
+    tri = np.array(list(range(n_clusters)) + list(range(n_clusters - 2, 0, -1)), dtype=np.int64)
+    return tri[(cube_x // 2) % period]
+
+
+def build_layout(nx, ny, nz, rank, world, n_clusters=1, cluster_axis="z"):
+    """Layout of `rank`: which cells it owns, in which order, where its ghost cells sit and what is exchanged.
+    cluster_axis: "z" = horizontal bands (remote neighbors share the cluster), "x" = bands across the slabs."""
     if nx % world:
         raise ValueError("nx must be a multiple of the number of ranks")
     nxl = nx // world
@@ -79,7 +94,7 @@ def build_layout(nx, ny, nz, rank, world, n_clusters=1):
             lo, hi = 0, nx
         mesh = CubeMesh(nx, ny, nz, lo, hi)
         own = (mesh.cube_x >= x_lo) & (mesh.cube_x < x_hi)
-    cluster = cluster_of_z(mesh.cube_z, nz, n_clusters)
+    cluster = cluster_of_z(mesh.cube_z, nz, n_clusters) if cluster_axis == "z" else cluster_of_x(mesh.cube_x, nx, n_clusters)
     nb = mesh.neighbors
     has = nb >= 0
     nb_own = np.where(has, own[np.maximum(nb, 0)], True)

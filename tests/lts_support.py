@@ -79,21 +79,35 @@ class NumpyLtsBackend:
             a0 = p.acc_row[r.start]
             self.acc[a0:a0 + na] = I[:na] if reset else self.acc[a0:a0 + na] + I[:na]
 
-    def exchange(self, c):
+    def exchange(self, c, reset=True):
         import torch
         dist, p = self.dist, self.plan
-        ops, bufs = [], []
+        ops, bufs, dbufs = [], [], []
+        tdt = torch.from_numpy(self.idofs[:1]).dtype
         for peer, side, idx in sorted(p.send[c], key=lambda r: r[1]):
             ops.append(dist.P2POp(dist.isend, torch.from_numpy(np.ascontiguousarray(self.idofs[idx])), peer, tag=2 * c + side))
+        for peer, side, rows in sorted(p.send_der[c], key=lambda r: r[1]):
+            fam = np.stack([d[rows] for d in self.derivs], 1)           # [cells, order, B, 9]
+            ops.append(dist.P2POp(dist.isend, torch.from_numpy(np.ascontiguousarray(fam)), peer, tag=64 + 2 * c + side))
         for peer, side, start, count in sorted(p.recv[c], key=lambda r: 1 - r[1]):
-            t = torch.empty((count,) + self.idofs.shape[1:], dtype=torch.from_numpy(self.idofs[:1]).dtype)
+            t = torch.empty((count,) + self.idofs.shape[1:], dtype=tdt)
             bufs.append((start, count, t))
             ops.append(dist.P2POp(dist.irecv, t, peer, tag=2 * c + (1 - side)))
+        for peer, side, row0, count in sorted(p.recv_der[c], key=lambda r: 1 - r[1]):
+            t = torch.empty((count, self.order) + self.idofs.shape[1:], dtype=tdt)
+            dbufs.append((row0, count, t))
+            ops.append(dist.P2POp(dist.irecv, t, peer, tag=64 + 2 * c + (1 - side)))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         for start, count, t in bufs:
             self.idofs[start:start + count] = t.numpy()
+        for row0, count, t in dbufs:
+            for d in range(self.order):
+                self.derivs[d][row0:row0 + count] = t.numpy()[:, d]
+        g, rows = p.ghost_acc[c]
+        if len(g):      # ghost cells read by a larger own cluster: sum of their two steps
+            self.acc[rows] = self.idofs[g] if reset else self.acc[rows] + self.idofs[g]
 
     def correct(self, c, r, coeffs_full, coeffs_sub):
         p, sl = self.plan, slice(r.start, r.end)
@@ -109,9 +123,8 @@ class NumpyLtsBackend:
             k = p.kind[sl, f]
             n_f = nb[sl, f]
             buf = self.idofs[n_f]                      # same cluster (local or ghost row): the integral of this step
-            nl = np.where(n_f < p.n, n_f, 0)
-            accm = (k == 0) & (n_f < p.n) & (p.cluster[nl] == c - 1) & (p.face_types[sl, f] == 0)
-            buf[accm] = self.acc[p.acc_row[nl][accm]]  # smaller cluster: sum over its two steps
+            accm = (k == 0) & (p.cluster_ext[n_f] == c - 1) & (p.face_types[sl, f] == 0)
+            buf[accm] = self.acc[p.acc_row[n_f][accm]]  # smaller cluster (own or ghost cell): sum over its two steps
             tm = k > 0
             buf[tm] = self.scratch[p.scratch_row[sl, f][tm]]
             Inb[:, f] = buf

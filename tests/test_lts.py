@@ -17,8 +17,8 @@ from seissol_b200 import mesh as M
 from seissol_b200 import partition as P
 
 
-def make_problem(order, dt, dims, ncl, scale=1e-2):
-    layout = P.build_layout(*dims, 0, 1, ncl)
+def make_problem(order, dt, dims, ncl, scale=1e-2, axis="z"):
+    layout = P.build_layout(*dims, 0, 1, ncl, cluster_axis=axis)
     plan = L.build_plan(layout, ncl)
     B = O.nbasis(order)
     Q = M.element_values(plan.gid, 9 * B, 0, 1.0, dt).reshape(plan.n, 9, B).transpose(0, 2, 1).copy()
@@ -72,14 +72,18 @@ def _free_port():
     return port
 
 
-def _lts_rank(rank, world, port, dims, ncl, steps, out):
+def _lts_rank(rank, world, port, dims, ncl, steps, out, axis="z"):
     order, dt = 4, np.float64
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
-    layout = P.build_layout(*dims, rank, world, ncl)
+    layout = P.build_layout(*dims, rank, world, ncl, cluster_axis=axis)
     plan = L.build_plan(layout, ncl)
+    if world > 1 and axis == "x":
+        # the slab boundaries separate different clusters: derivative families travel, ghost buffers are accumulated
+        assert sum(len(v) for v in plan.send_der.values()) + sum(len(v) for v in plan.recv_der.values()) > 0
+        assert sum(len(g) for g, _ in plan.ghost_acc.values()) + sum(len(v) for v in plan.recv_der.values()) > 0
     B = O.nbasis(order)
     Q = M.element_values(plan.gid, 9 * B, 0, 1.0, dt).reshape(plan.n, 9, B).transpose(0, 2, 1).copy()
     li = M.element_values(plan.gid, 396, 1, 1e-2, dt)
@@ -98,13 +102,16 @@ def _lts_rank(rank, world, port, dims, ncl, steps, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_lts_matches_single_rank(world, tmp_path):
-    """LTS on the x-slab partition (per-cluster halo exchange, gloo) reproduces the single-rank LTS run."""
-    dims, ncl, steps = (8, 2, 10), 3, 2
+@pytest.mark.parametrize("world,axis", [(2, "z"), (4, "z"), (2, "x"), (4, "x")])
+def test_partitioned_lts_matches_single_rank(world, axis, tmp_path):
+    """LTS on the x-slab partition (per-cluster halo exchange, gloo) reproduces the single-rank LTS run.  axis "z": the
+    remote neighbors share the time cluster (buffers travel); axis "x": every slab boundary separates two clusters
+    (derivative families travel to the smaller cluster's side, the larger cluster's side accumulates the ghost buffers:
+    DirectGhostTimeCluster.cpp:22-105, LtsSetup.cpp:115-189)."""
+    dims, ncl, steps = ((8, 2, 10) if axis == "z" else (8, 2, 2)), 3, 2
     out = str(tmp_path)
-    _lts_rank(0, 1, 0, dims, ncl, steps, out)
-    mp.spawn(_lts_rank, args=(world, _free_port(), dims, ncl, steps, out), nprocs=world, join=True)
+    _lts_rank(0, 1, 0, dims, ncl, steps, out, axis)
+    mp.spawn(_lts_rank, args=(world, _free_port(), dims, ncl, steps, out, axis), nprocs=world, join=True)
     q1, g1 = np.load(os.path.join(out, "q_1_0.npy")), np.load(os.path.join(out, "gid_1_0.npy"))
     ref = np.empty_like(q1)
     ref[g1] = q1
@@ -147,16 +154,16 @@ def test_lts_cuda_matches_brute_force(built_library, order, dt, bar, faceproj):
     assert be.launches > 0
 
 
-def _cuda_lts_rank(rank, world, port, out, faceproj=False):
+def _cuda_lts_rank(rank, world, port, out, faceproj=False, axis="z"):
     """One GPU per rank: partitioned LTS through the C ABI with NCCL; rank-local result saved for the comparison."""
     from seissol_b200 import api
-    order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
+    order, dt, ncl, dims = 4, np.float32, 3, ((8, 2, 10) if axis == "z" else (8, 2, 2))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    layout = P.build_layout(*dims, rank, world, ncl)
+    layout = P.build_layout(*dims, rank, world, ncl, cluster_axis=axis)
     plan = L.build_plan(layout, ncl)
     ctx = api.Context(order, 4)
     Q = M.element_values(plan.gid, 9 * ctx.B, 0, 1.0, dt).reshape(plan.n, 9, ctx.B)
@@ -178,16 +185,18 @@ def _cuda_lts_rank(rank, world, port, out, faceproj=False):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("axis", ["z", "x"])
 @pytest.mark.parametrize("faceproj", [False, True])
-def test_partitioned_lts_cuda_two_gpus(built_library, tmp_path, faceproj):
+def test_partitioned_lts_cuda_two_gpus(built_library, tmp_path, faceproj, axis):
     """2 GPUs, NCCL: the partitioned LTS run through the CUDA kernels matches the brute-force LTS of the whole mesh
-    (faceproj: the halo carries face projections)."""
+    (faceproj: the halo carries face projections; axis "x": the slab boundaries separate different time clusters, so
+    derivative families travel and ghost buffers are accumulated on arrival)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    order, dt, ncl, dims = 4, np.float32, 3, (8, 2, 10)
+    order, dt, ncl, dims = 4, np.float32, 3, ((8, 2, 10) if axis == "z" else (8, 2, 2))
     out = str(tmp_path)
-    mp.spawn(_cuda_lts_rank, args=(2, _free_port(), out, faceproj), nprocs=2, join=True)
-    plan, Q, li, ni = make_problem(order, dt, dims, ncl)
+    mp.spawn(_cuda_lts_rank, args=(2, _free_port(), out, faceproj, axis), nprocs=2, join=True)
+    plan, Q, li, ni = make_problem(order, dt, dims, ncl, axis=axis)
     tab = O.load_tables(order, dt)
     star = O.star_dense(li[:, :72].reshape(-1, 3, 24), tab["star_pattern"])
     want = Q
