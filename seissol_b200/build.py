@@ -122,6 +122,7 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
             print(f"[build] linked {lib}", flush=True)
     if variant is None:
         build_host(lib, verbose)
+        build_lts_host(lib, verbose)
     return lib
 
 
@@ -142,6 +143,42 @@ def build_host(lib, verbose=True):
         raise RuntimeError(f"host build failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         print(f"[build] built {exe}", flush=True)
+    return exe
+
+
+def build_lts_host(lib, verbose=True):
+    """C++ LTS host (host/ssb_lts.hpp: plan, rate-2 schedule, NCCL halo) + the ssb_lts_proxy executable.  NCCL comes
+    from the system (libnccl-dev) or from the wheel torch brings; without either the single-rank build remains."""
+    root = os.path.join(HERE, "..")
+    src = os.path.join(root, "host", "lts_main.cpp")
+    exe = os.path.join(LIBDIR, "ssb_lts_proxy")
+    deps = [src, os.path.join(root, "host", "ssb_lts.hpp"), os.path.join(root, "host", "ssb_host.hpp"),
+            os.path.join(root, "include", "seissol_b200.h"), lib]
+    if not _newer(exe, deps):
+        return exe
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    nccl_flags = []
+    candidates = [("/usr/include", "/usr/lib/x86_64-linux-gnu")]
+    try:
+        import nvidia.nccl as _n
+        base = os.path.dirname(_n.__file__) if getattr(_n, "__file__", None) else list(_n.__path__)[0]
+        candidates.append((os.path.join(base, "include"), os.path.join(base, "lib")))
+    except Exception:
+        pass
+    for inc, libdir in candidates:
+        so = [x for x in (os.listdir(libdir) if os.path.isdir(libdir) else []) if x.startswith("libnccl.so")]
+        if os.path.exists(os.path.join(inc, "nccl.h")) and so:
+            link = "-lnccl" if "libnccl.so" in so else f"-l:{sorted(so)[0]}"
+            nccl_flags = ["-DSSB_WITH_NCCL", f"-I{inc}", f"-L{libdir}", link, f"-Wl,-rpath,{libdir}"]
+            break
+    cmd = ["g++", "-std=c++17", "-O2", src, f"-I{os.path.join(root, 'include')}", f"-I{os.path.join(root, 'host')}",
+           f"-I{os.path.join(cuda, 'include')}", f"-L{LIBDIR}", "-lseissol_b200", f"-L{os.path.join(cuda, 'lib64')}",
+           "-lcudart", "-Wl,-rpath,$ORIGIN", "-pthread", *nccl_flags, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"LTS host build failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"[build] built {exe}" + (" (NCCL)" if nccl_flags else " (single rank: no NCCL found)"), flush=True)
     return exe
 
 

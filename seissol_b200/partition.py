@@ -166,3 +166,21 @@ def build_layout(nx, ny, nz, rank, world, n_clusters=1, cluster_axis="z"):
             "interior": (n_copy + int(ic[0]), n_copy + int(ic[-1]) + 1) if len(ic) else (n_copy, n_copy),
         }
     return lay
+
+
+def export_layout(layout, path):
+    """RankLayout -> the binary file host/ssb_lts.hpp::Layout::read loads (little endian; int64 header
+    {magic "SSBLTS01", rank, world, n_own, n_ghost, n_clusters, #send, #recv}, then gid, cluster, neighbors (int64),
+    face_rel, face_types (uint8), send and recv regions as {peer, side, cluster, start, count} int64 records)."""
+    n_clusters = int(layout.cluster.max(initial=0)) + 1 if len(layout.cluster) else 1
+    n_clusters = max(n_clusters, len(layout.cluster_ranges))
+    with open(path, "wb") as f:
+        np.array([0x5353424C54533031, layout.rank, layout.world, layout.n_own, layout.n_ghost, n_clusters,
+                  len(layout.send), len(layout.recv)], dtype=np.int64).tofile(f)
+        layout.gid.astype(np.int64).tofile(f)
+        layout.cluster.astype(np.int64).tofile(f)
+        np.ascontiguousarray(layout.neighbors, dtype=np.int64).tofile(f)
+        np.ascontiguousarray(layout.face_rel, dtype=np.uint8).tofile(f)
+        np.ascontiguousarray(layout.face_types, dtype=np.uint8).tofile(f)
+        for regs in (layout.send, layout.recv):
+            np.array([[r.peer, r.side, r.cluster, r.start, r.count] for r in regs], dtype=np.int64).reshape(-1, 5).tofile(f)
