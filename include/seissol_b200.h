@@ -231,7 +231,13 @@ int ssb_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, const void* const* godunov, con
  *                 per-cell computeAder :50-120);
  * ssb_visco_local replaces Local::computeBatchedIntegral (src/Kernels/LinearCKAnelastic/Local.cpp:112-250, per-cell :63-110);
  * ssb_visco_neigh replaces Neighbor::computeBatchedNeighborsIntegral (src/Kernels/LinearCKAnelastic/Neighbor.cpp:162-260,
- *                 per-cell :71-130); regular faces only in this revision (DR faces are skipped). */
+ *                 per-cell :71-130), regular faces;
+ * ssb_visco_neigh_dr: its DynamicRupture branch (:107-115, batched :171-234): for every face of FaceType DynamicRupture
+ *                 Qext += V3mTo2nTWDivM(side, rel) . godunov . fluxSolver, then kernel::neighbor (Q += Qext[:, :9],
+ *                 Qane += w[m] Qext[:, 9:]) -- linear in Qext, hence a launch of its own next to ssb_visco_neigh.
+ *                 godunov: device [n][4] pointers to the imposed state of the face [9][ppad] (CellDRMapping::godunov,
+ *                 NULL = no fault face); flux_solver: [n][4] pointers to the 9 x 15 flux solver (column-major
+ *                 [c + 9 q]); side_rel: uint8 [n][4][2] = {side, faceRelation}; ppad = ssb_query()[23]. */
 int ssb_visco_ader(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
                    ssb_array_t local_int, const double* coeffs, long long n, void* stream);
 int ssb_visco_local(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t idofs, ssb_array_t idofs_ane,
@@ -239,6 +245,10 @@ int ssb_visco_local(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_ar
 int ssb_visco_neigh(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, const void* const* nb_ptrs,
                     const long long* nb_idx, ssb_array_t idofs, ssb_array_t neigh_int, const uint8_t* face_types,
                     const uint8_t* face_rel, long long n, const int* perm, void* stream);
+
+int ssb_visco_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t neigh_int,
+                       const void* const* godunov, const void* const* flux_solver, const uint8_t* side_rel,
+                       const uint8_t* face_types, long long n, void* stream);
 
 const char* ssb_error_string(int code);
 const char* ssb_version(void);

@@ -272,6 +272,26 @@ class ViscoRefLib:
                               _p(self._c(w)), _p(fr), _p(ft))
         return self.from_ref(q), self.ane_from_ref(qa)
 
+    def neigh_dr(self, Q, Qane, Iall, neighbors, Aminus, w, face_rel, face_types, dr):
+        """ssrefv_neigh with the DynamicRupture branch; dr as oracle.visco.neighbor."""
+        n = Q.shape[0]
+        q, qa = self.to_ref(Q), self.ane_to_ref(Qane)
+        nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+        fr = np.ascontiguousarray(face_rel, dtype=np.uint8)
+        ft = np.ascontiguousarray(face_types, dtype=np.uint8)
+        self.lib.ssrefv_qinterp_size.restype = ctypes.c_int64
+        ldp = int(self.lib.ssrefv_qinterp_size()) // 9
+        g = dr["godunov"]
+        god = np.zeros((g.shape[0], 9, ldp), dtype=self.dtype)
+        god[:, :, :g.shape[1]] = g.transpose(0, 2, 1)
+        fs = np.ascontiguousarray(dr["fluxSolver"].transpose(0, 2, 1), dtype=self.dtype)     # column-major 9 x 15
+        self.lib.ssrefv_neigh_dr(ctypes.c_int64(n), _p(q), _p(qa), _p(self.to_ref(Iall)), _p(nb), _p(self._c(Aminus)),
+                                 _p(self._c(w)), _p(fr), _p(ft), _p(god), _p(fs),
+                                 _p(np.ascontiguousarray(dr["index"], dtype=np.int64)),
+                                 _p(np.ascontiguousarray(dr["side"], dtype=np.uint8)),
+                                 _p(np.ascontiguousarray(dr["rel"], dtype=np.uint8)))
+        return self.from_ref(q), self.ane_from_ref(qa)
+
     def threads(self):
         return int(self.lib.ssrefv_threads())
 

@@ -85,10 +85,20 @@ def local(tab, Q, Qane, I, Iane, star, Aplus, E, w, W, face_types=None):
     return Q_new, Qane_new
 
 
-def neighbor(tab, Q, Qane, Iall, neighbors, Aminus, w, face_rel, face_types=None):
+def neighbor(tab, Q, Qane, Iall, neighbors, Aminus, w, face_rel, face_types=None, dr=None):
     """Neighbor::computeNeighborsIntegral (LinearCKAnelastic/Neighbor.cpp:71-130): neighborFluxExt(h, j, i) into
-    Qext, then kernel::neighbor (viscoelastic2.py:317-334): Qane += w[m] Qext[:, 9:]; Q += Qext[:, :9]."""
+    Qext, then kernel::neighbor (viscoelastic2.py:317-334): Qane += w[m] Qext[:, 9:]; Q += Qext[:, :9].
+    DynamicRupture faces (:107-115): Qext += V3mTo2nTWDivM(side, rel) . godunov . fluxSolver (dynamic_rupture.py:174-191
+    with the 9 x 15 flux solver of the extended quantities); `dr` = dict(godunov [m, P, 9], fluxSolver [m, 9, 15],
+    index [n, 4], side [n, 4], rel [n, 4])."""
     ext = np.zeros(Q.shape[:2] + (NE,), dtype=Q.dtype)
+    if dr is not None and face_types is not None:
+        for i in range(4):
+            m = face_types[:, i] == 3
+            if m.any():
+                idx = dr["index"][m, i]
+                mat = tab["V3mTo2nTWDivM"][dr["side"][m, i] + 4 * dr["rel"][m, i]]
+                ext[m] += np.matmul(mat, np.matmul(dr["godunov"][idx], dr["fluxSolver"][idx]))
     for i in range(4):
         j = face_rel[:, i, 0]
         h = face_rel[:, i, 1]

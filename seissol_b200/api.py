@@ -18,7 +18,7 @@ SYMBOLS = [
     "ssb_ader", "ssb_local", "ssb_ader_local", "ssb_taylor", "ssb_lts_accumulate", "ssb_neigh",
     "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj", "ssb_taylor_faceproj", "ssb_accumulate_rows",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
-    "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh",
+    "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh", "ssb_visco_neigh_dr",
     "ssb_error_string", "ssb_version",
 ]
 
@@ -96,6 +96,7 @@ def load_library():
     lib.ssb_visco_ader.argtypes = [P, A, A, A, A, A, P, LL, P]
     lib.ssb_visco_local.argtypes = [P, A, A, A, A, A, P, LL, P]
     lib.ssb_visco_neigh.argtypes = [P, A, A, P, P, A, A, P, P, LL, P, P]
+    lib.ssb_visco_neigh_dr.argtypes = [P, A, A, A, P, P, P, P, LL, P]
     _lib = lib
     return lib
 
@@ -244,6 +245,10 @@ class Context:
                     perm=None, stream=None):
         _check(self.lib.ssb_visco_neigh(self.handle, dofs, dofs_ane, _ptr(nb_ptrs), _ptr(nb_idx), idofs, neigh_int,
                                         _ptr(face_types), _ptr(face_rel), n, _ptr(perm), _stream(stream)))
+
+    def visco_neigh_dr(self, dofs, dofs_ane, neigh_int, godunov_ptrs, flux_solver_ptrs, side_rel, face_types, n, stream=None):
+        _check(self.lib.ssb_visco_neigh_dr(self.handle, dofs, dofs_ane, neigh_int, _ptr(godunov_ptrs), _ptr(flux_solver_ptrs),
+                                           _ptr(side_rel), _ptr(face_types), n, _stream(stream)))
 
     # -- dynamic rupture ------------------------------------------------------------------------
     def dr_interp(self, der_plus, der_minus, tinv_t, face_info, q_plus, q_minus, coeffs, n, perm=None, stream=None):

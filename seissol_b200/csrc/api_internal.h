@@ -97,6 +97,7 @@ struct ViscoKernelSet {
   int (*ader)(const ViscoLocalParams&, cudaStream_t);
   int (*local)(const ViscoLocalParams&, cudaStream_t);
   int (*neigh)(const ViscoNeighParams&, cudaStream_t);
+  int (*neighDr)(const ViscoNeighDrParams&, cudaStream_t);
 };
 const ViscoKernelSet* viscokernelset_o5_f32();
 const ViscoKernelSet* viscokernelset_o5_f64();

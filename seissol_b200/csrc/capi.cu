@@ -229,7 +229,8 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
   }
   c->visco = visco;
   c->dr = visco != nullptr ? nullptr : lookupDr(order, real_size);
-  c->ppad = c->dr != nullptr ? c->dr->PP : 0;
+  // fault points per face padded to 4 (viscoelastic2: only the nodal flux of the imposed state is on this path)
+  c->ppad = c->dr != nullptr ? c->dr->PP : ((order + 1) * (order + 1) + 3) / 4 * 4;
   c->order = order;
   c->realSize = real_size;
   c->equation = equation;
@@ -269,10 +270,9 @@ int ssb_layout_reference(ssb_ctx* c) {
     return SSB_EINVAL;
   }
   referenceLayout(c);
-  if (c->dr != nullptr) {
-    const int per = 64 / c->realSize;
-    c->ppad = (c->dr->P + per - 1) / per * per;
-  }
+  const int per = 64 / c->realSize;
+  const int points = c->dr != nullptr ? c->dr->P : (c->order + 1) * (c->order + 1);
+  c->ppad = (points + per - 1) / per * per;
   return 0;
 }
 
@@ -291,7 +291,7 @@ int ssb_query(const ssb_ctx* c, int* out) {
   }
   out[20] = c->ksLocal->eLocal;
   out[21] = c->ksNeigh->eNeigh;
-  out[22] = c->dr != nullptr ? c->dr->P : 0;
+  out[22] = c->dr != nullptr ? c->dr->P : (c->order + 1) * (c->order + 1);
   out[23] = c->ppad;
   return 0;
 }
@@ -755,6 +755,36 @@ int ssb_visco_neigh(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, const vo
   p.n = n;
   p.ldg = c->ldq;
   return c->visco->neigh(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_visco_neigh_dr(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_array_t neigh_int,
+                       const void* const* godunov, const void* const* flux_solver, const uint8_t* side_rel,
+                       const uint8_t* face_types, long long n, void* stream) {
+  if (c == nullptr || c->visco == nullptr || n < 0) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  if (godunov == nullptr || flux_solver == nullptr || side_rel == nullptr || face_types == nullptr) {
+    return SSB_EINVAL;
+  }
+  ViscoNeighDrParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  p.dofsAne = conv(dofs_ane);
+  p.neighInt = conv(neigh_int);
+  if (!p.dofs.present() || !p.dofsAne.present() || !p.neighInt.present()) {
+    return SSB_EINVAL;
+  }
+  p.godunov = godunov;
+  p.fluxSolver = flux_solver;
+  p.sideRel = side_rel;
+  p.faceTypes = face_types;
+  p.n = n;
+  p.ldg = c->ldq;
+  p.ppad = c->ppad;
+  return c->visco->neighDr(p, static_cast<cudaStream_t>(stream));
 }
 
 const char* ssb_error_string(int code) {

@@ -76,6 +76,21 @@ int localEntry(const ViscoLocalParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
+struct GenDr {
+  static constexpr int kP = SSB_CAT(gen_dr_o, SSB_ORDER)::kP;
+  template <typename R>
+  __device__ __forceinline__ static const R* nodalFluxTable() { return SSB_CAT(gen_dr_o, SSB_ORDER)::nodalFluxTable<R>(); }
+};
+
+int neighDrEntry(const ViscoNeighDrParams& p, cudaStream_t stream) {
+  if (p.n <= 0) {
+    return 0;
+  }
+  constexpr int W = 4;   // warps = elements per CTA
+  k_visco_neigh_dr<Real, Gen, GenDr, W><<<unsigned((p.n + W - 1) / W), 32 * W, 0, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
 int neighEntry(const ViscoNeighParams& p, cudaStream_t stream) {
   static SmemConfig done;
   auto kern = k_visco_neigh<Real, Gen, VE>;
@@ -90,7 +105,8 @@ int neighEntry(const ViscoNeighParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
-const ViscoKernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, VE, aderEntry, localEntry, neighEntry};
+const ViscoKernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, VE, aderEntry, localEntry, neighEntry,
+                             neighDrEntry};
 
 }  // namespace
 

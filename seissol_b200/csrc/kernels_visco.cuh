@@ -520,4 +520,127 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_neig
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_visco_neigh_dr: the DynamicRupture branch of the viscoelastic neighbor integral
+// (src/Kernels/LinearCKAnelastic/Neighbor.cpp:107-115: dynamicRupture::kernel::nodalFlux into Qext, then kernel::neighbor):
+//   Qext = sum over the element's fault faces of  V3mTo2nTWDivM(side, rel) . godunov . fluxSolver      [B x 15]
+//   Q += Qext[:, :9];  Qane[:, p, m] += w[m] Qext[:, 9 + p]
+// kernel::neighbor is linear in Qext, so regular faces (k_visco_neigh) and fault faces are two launches.
+// One warp per element like k_neigh_dr (kernels_dr.cuh): lanes are the fault points for T = godunov . fluxSolver
+// [P x 15] (shared memory), then rows k = lane, lane + 32 of W(variant) . T from the dense table of the operator.
+template <typename R, typename G, typename GD, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_visco_neigh_dr(const ViscoNeighDrParams p) {
+  constexpr int B = G::kB, P = GD::kP;
+  constexpr int TS = 16;  // reals per point of T in shared memory (15 padded to 16: four 128-bit words)
+  __shared__ __align__(16) R sT[WARPS][2 * 32 * TS];
+  __shared__ __align__(16) R sFs[WARPS][136];
+  static_assert(P <= 64 && B <= 64, "two points / rows per lane");
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long el = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  if (el >= p.n) {
+    return;
+  }
+  const R* const table = GD::template nodalFluxTable<R>();
+  const uchar4 ft = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
+  R acc[2][kVNE];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int q = 0; q < kVNE; ++q) {
+      acc[r][q] = R(0);
+    }
+  }
+  bool any = false;
+#pragma unroll 1
+  for (int f = 0; f < 4; ++f) {
+    const uint8_t ty = f == 0 ? ft.x : (f == 1 ? ft.y : (f == 2 ? ft.z : ft.w));
+    const R* god = static_cast<const R*>(p.godunov[4 * el + f]);
+    if (ty != 3 || god == nullptr) {
+      continue;  // warp-uniform
+    }
+    any = true;
+    const R* fs = static_cast<const R*>(p.fluxSolver[4 * el + f]);
+    const int variant = p.sideRel[8 * el + 2 * f] + 4 * p.sideRel[8 * el + 2 * f + 1];
+    __syncwarp();
+    for (int i = lane; i < 9 * kVNE; i += 32) {
+      sFs[warp][i] = fs[i];
+    }
+    __syncwarp();
+    // ---- step 1: T = godunov . fluxSolver for the points lane, lane + 32
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int pt = lane + 32 * half;
+      R t[TS];
+#pragma unroll
+      for (int q = 0; q < TS; ++q) {
+        t[q] = R(0);
+      }
+      if (pt < P) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const R gv = god[c * p.ppad + pt];
+#pragma unroll
+          for (int q = 0; q < kVNE; ++q) {
+            t[q] = fma(gv, sFs[warp][c + 9 * q], t[q]);
+          }
+        }
+      }
+      R* dst = &sT[warp][pt * TS];
+#pragma unroll
+      for (int q4 = 0; q4 < TS / 4; ++q4) {
+        st4(dst + 4 * q4, t[4 * q4], t[4 * q4 + 1], t[4 * q4 + 2], t[4 * q4 + 3]);
+      }
+    }
+    __syncwarp();
+    // ---- step 2: acc += W(variant) . T
+    const R* w = table + static_cast<size_t>(variant) * P * 64 + lane;
+#pragma unroll 4
+    for (int pt = 0; pt < P; ++pt) {
+      const R w0 = w[pt * 64];
+      const R w1 = w[pt * 64 + 32];
+      R t[TS];
+#pragma unroll
+      for (int q4 = 0; q4 < TS / 4; ++q4) {
+        R u[4];
+        ld4(u, &sT[warp][pt * TS + 4 * q4]);
+        t[4 * q4] = u[0]; t[4 * q4 + 1] = u[1]; t[4 * q4 + 2] = u[2]; t[4 * q4 + 3] = u[3];
+      }
+#pragma unroll
+      for (int q = 0; q < kVNE; ++q) {
+        acc[0][q] = fma(w0, t[q], acc[0][q]);
+        acc[1][q] = fma(w1, t[q], acc[1][q]);
+      }
+    }
+  }
+  if (!any) {
+    return;
+  }
+  R* const dofs = static_cast<R*>(const_cast<void*>(p.dofs.at(el)));
+  R* const ane = static_cast<R*>(const_cast<void*>(p.dofsAne.at(el)));
+  const R* const wv = static_cast<const R*>(p.neighInt.at(el)) + 4 * kVA;
+  R wm[kVM];
+#pragma unroll
+  for (int m = 0; m < kVM; ++m) {
+    wm[m] = wv[m];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int k = lane + 32 * r;
+    if (k < B) {
+#pragma unroll
+      for (int q = 0; q < kNQ; ++q) {
+        dofs[q * p.ldg + k] += acc[r][q];
+      }
+#pragma unroll
+      for (int m = 0; m < kVM; ++m) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          ane[(a + 6 * m) * p.ldg + k] += wm[m] * acc[r][kNQ + a];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ssb

@@ -139,6 +139,17 @@ struct ViscoLocalParams {
   double coeffs[8];
 };
 
+struct ViscoNeighDrParams {
+  ElemArray dofs, dofsAne, neighInt;
+  const void* const* godunov;      // [n][4] imposed state of the fault face, [9][ppad] (CellDRMapping::godunov) or null
+  const void* const* fluxSolver;   // [n][4] 9 x 15 flux solver of the extended quantities, column-major [c + 9 q]
+  const uint8_t* sideRel;          // [n][4][2] {side, faceRelation}
+  const uint8_t* faceTypes;        // [n][4]
+  long long n;
+  int ldg;
+  int ppad;
+};
+
 struct ViscoNeighParams {
   ElemArray dofs, dofsAne, idofs, neighInt;
   const void* const* nbPtrs;

@@ -140,3 +140,47 @@ def test_visco_empty_batch_and_reference_layout(gpu):
         assert rel_l2(dd.q_to_logical(dd.dofs), want["Q"]) < tol(dt)
         assert rel_l2(dd.ane_to_logical(dd.dofs_ane), want["Qane"]) < tol(dt)
     del star, E
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,m", [(5, 7), (211, 300)])
+def test_visco_neigh_dr_matches_oracle(gpu, dt, n, m):
+    """ssb_visco_neigh + ssb_visco_neigh_dr = Neighbor::computeNeighborsIntegral of the viscoelastic2 build with
+    DynamicRupture faces (LinearCKAnelastic/Neighbor.cpp:71-130): regular faces and the nodal flux of the imposed
+    fault state against the oracle (whose DR branch is pinned against the reference's generated kernels)."""
+    from test_oracle_visco import visco_dr_case
+    torch, api, proxy = gpu
+    ctx = api.Context(5, np.dtype(dt).itemsize, equation=1, mechanisms=3)
+    tab = O.load_tables(5, dt)
+    rng = np.random.default_rng(31)
+    P = 36
+    assert ctx.P == P and ctx.ppad >= P
+    d = V.proxy_data(5, n, dt, seed=200 + n)
+    d["face_types"], dr = visco_dr_case(rng, n, m, P, dt)
+    I = rng.uniform(-1, 1, d["Q"].shape).astype(dt)
+    d["I"] = I
+    data = proxy.ViscoProxyData.from_host(ctx, d)
+    dev = data.dofs.device
+    es = np.dtype(dt).itemsize
+    god = np.zeros((m, 9, ctx.ppad), dtype=dt)
+    god[:, :, :P] = dr["godunov"].transpose(0, 2, 1)
+    god_d = torch.from_numpy(god).to(dev)
+    fs_d = torch.from_numpy(np.ascontiguousarray(dr["fluxSolver"].transpose(0, 2, 1)).reshape(m, 135)).to(dev)
+    is_dr = d["face_types"] == 3
+    gp = np.where(is_dr, god_d.data_ptr() + dr["index"] * 9 * ctx.ppad * es, 0).astype(np.int64)
+    fp = np.where(is_dr, fs_d.data_ptr() + dr["index"] * 135 * es, 0).astype(np.int64)
+    sr = np.stack([dr["side"], dr["rel"]], -1).astype(np.uint8)
+    k = proxy.ViscoProxyKernels(ctx, data)
+    k.neigh()
+    ctx.visco_neigh_dr(api.strided(data.dofs), api.strided(data.dofs_ane), api.strided(data.neigh_int),
+                       torch.from_numpy(gp).to(dev), torch.from_numpy(fp).to(dev), torch.from_numpy(sr).to(dev),
+                       data.face_types, n)
+    torch.cuda.synchronize()
+    qn, qan = V.neighbor(tab, d["Q"], d["Qane"], I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"],
+                         d["face_types"], dr=dr)
+    q0, qa0 = V.neighbor(tab, d["Q"], d["Qane"], I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"],
+                         d["face_types"])
+    assert np.linalg.norm(qn - q0) > 1e-3 * np.linalg.norm(q0)      # the fault faces do contribute
+    assert rel_l2(data.q_to_logical(data.dofs), qn) < tol(dt)
+    assert rel_l2(data.ane_to_logical(data.dofs_ane), qan) < tol(dt)
+    assert rel_l2(data.q_to_logical(data.dofs) - q0, qn - q0) < 50 * tol(dt)

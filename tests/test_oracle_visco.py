@@ -74,3 +74,40 @@ def test_visco_oracle_matches_reference_library(cfg, dt):
     qn, qan = V.neighbor(tab, ql, qal, I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"], d["face_types"])
     qnr, qanr = R.neigh(qlr, qalr, Ir, d["neighbors"], d["Aminus"], d["w"], d["face_rel"], d["face_types"])
     assert rel_l2(qn, qnr) < tol(dt) and rel_l2(qan, qanr) < tol(dt)
+
+
+def visco_dr_case(rng, n, m, P, dt):
+    """m fault faces attached to random (cell, face) slots: imposed states, 9 x 15 flux solvers, side / relation."""
+    face_types = np.zeros((n, 4), dtype=np.uint8)
+    index = np.zeros((n, 4), dtype=np.int64)
+    slots = rng.choice(4 * n, size=m, replace=False)
+    face_types.ravel()[slots] = 3
+    index.ravel()[slots] = np.arange(m)
+    return face_types, {
+        "godunov": rng.uniform(-1, 1, (m, P, 9)).astype(dt),
+        "fluxSolver": (rng.uniform(-1, 1, (m, 9, 15)) * 1e-2).astype(dt),
+        "index": index,
+        "side": rng.integers(0, 4, (n, 4)).astype(np.uint8),
+        "rel": rng.integers(0, 4, (n, 4)).astype(np.uint8),
+    }
+
+
+@pytest.mark.parametrize("cfg,dt", CASES)
+def test_visco_dr_nodal_flux_matches_reference_library(cfg, dt):
+    """The DynamicRupture branch of the viscoelastic neighbor integral (LinearCKAnelastic/Neighbor.cpp:107-115): the
+    oracle against the reference's generated dynamicRupture::kernel::nodalFlux + kernel::neighbor."""
+    if not ref_lib.available(cfg):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    R = ref_lib.ViscoRefLib(cfg)
+    tab = O.load_tables(5, dt)
+    rng = np.random.default_rng(12)
+    n, m, P = 29, 40, 36
+    d = V.proxy_data(5, n, dt, seed=6)
+    ft, dr = visco_dr_case(rng, n, m, P, dt)
+    I = rng.uniform(-1, 1, d["Q"].shape).astype(dt)
+    qn, qan = V.neighbor(tab, d["Q"], d["Qane"], I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"], ft, dr=dr)
+    qnr, qanr = R.neigh_dr(d["Q"], d["Qane"], I, d["neighbors"], d["Aminus"], d["w"], d["face_rel"], ft, dr)
+    assert rel_l2(qn, qnr) < tol(dt) and rel_l2(qan, qanr) < tol(dt)
+    q0, qa0 = V.neighbor(tab, d["Q"], d["Qane"], I, d["neighbors"], V.flux_dense(d["Aminus"]), d["w"], d["face_rel"], ft)
+    assert rel_l2(qn - q0, qnr - q0) < 10 * tol(dt) and rel_l2(qan - qa0, qanr - qa0) < 10 * tol(dt)   # the DR part itself
+    assert np.linalg.norm(qn - q0) > 1e-3 * np.linalg.norm(q0)
