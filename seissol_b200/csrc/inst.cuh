@@ -121,6 +121,9 @@ int launchLocal5(const LocalParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
+  if (p.n >= (1ll << 31)) {
+    return -1;   // SSB_EINVAL: generation 5 keeps element ids in 32 bits (one GPU holds ~2e7 elements)
+  }
   const long long batches = (p.n + EL - 1) / EL;
   const long long resident = static_cast<long long>(SSB_MINB_LOCAL5) * smCount();
   const unsigned grid = static_cast<unsigned>(batches < resident ? batches : resident);

@@ -1,4 +1,10 @@
 // Kernel instantiation: elastic, order 6, float.
+// k_neigh_fp: 14 elements per CTA, three resident CTAs per SM (two CTAs of 21: 2.63 ms, three of 14: 2.53 ms at 1 M elements:
+// the kernel waits on its gather, a third independent CTA covers more of it)
+#ifndef SSB_E_NEIGHFP
+#define SSB_E_NEIGHFP 14
+#define SSB_MINB_NEIGHFP 3
+#endif
 #include "gen/ops_o6.cuh"
 #include "gen/tc_o6.cuh"
 #define SSB_HAVE_TC 1

@@ -307,9 +307,11 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
   __syncthreads();
 
   const long long nBatches = (p.n + E - 1) / E;
-  auto elemOf = [&](long long batch, int e) -> long long {
+  // element ids as 32-bit values inside the kernel (the launcher rejects batches of 2^31 elements and more): four
+  // 64-bit ids are live across the whole batch, and the kernel sits at its register limit
+  auto elemOf = [&](long long batch, int e) -> int {
     const long long sl = batch * E + e;
-    return (batch < nBatches && sl < p.n) ? (p.perm != nullptr ? p.perm[sl] : sl) : -1;
+    return (batch < nBatches && sl < p.n) ? (p.perm != nullptr ? p.perm[sl] : static_cast<int>(sl)) : -1;
   };
   const bool wantProj = p.faceProj.present();
   const int r0 = kStarRow[q][0], r1 = kStarRow[q][1], r2 = kStarRow[q][2];
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
   if (batch >= nBatches) {
     return;
   }
-  long long myElem = le >= 0 ? elemOf(batch, le) : -1;
+  int myElem = le >= 0 ? elemOf(batch, le) : -1;
   if (le >= 0) {
     if (myElem >= 0) {
       mbar_arrive_expect_tx(bar, TEN * sizeof(R));
@@ -327,34 +329,37 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
       mbar_arrive_expect_tx(bar, 0);
     }
   }
-  long long el = active ? elemOf(batch, g) : -1;
+  int el = active ? elemOf(batch, g) : -1;
   const R* LI = el >= 0 ? static_cast<const R*>(p.localInt.at(el)) : nullptr;
+  const int sCnt = kStarCnt[q], sOff = kStarOff[q];   // loop invariant: looked up once (they are loads from a table)
   R s[3][3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      s[j][c] = (LI != nullptr && c < kStarCnt[q]) ? LI[24 * j + kStarOff[q] + c] : R(0);
+      s[j][c] = (LI != nullptr && c < sCnt) ? LI[24 * j + sOff + c] : R(0);
     }
   }
+  auto faceTypesOf = [&](int e) -> uchar4 {
+    return (p.faceTypes != nullptr && e >= 0) ? *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * e) : make_uchar4(0, 0, 0, 0);
+  };
+  uchar4 ft = faceTypesOf(el);
 
   uint32_t phase = 0;
   for (; batch < nBatches; batch += gridDim.x) {
     const long long nextBatch = batch + gridDim.x;
     const bool haveNext = nextBatch < nBatches;
-    const long long nextMy = (haveNext && le >= 0) ? elemOf(nextBatch, le) : -1;
-    const long long nextEl = (haveNext && active) ? elemOf(nextBatch, g) : -1;
-    const R* nextLI = nextEl >= 0 ? static_cast<const R*>(p.localInt.at(nextEl)) : nullptr;
-
+    // the next batch's element ids, integration-data pointer and face types are requested at the top of face 2 and
+    // consumed at face 3 / the bottom of the loop: early enough to hide the DRAM round trips (a load that is used right
+    // away cost 9 % of the warp samples), late enough not to hold five registers through the volume stage
+    int nextMy = -1, nextEl = -1;
+    const R* nextLI = nullptr;
+    uchar4 ftNext = make_uchar4(0, 0, 0, 0);
     bool skipFace[4];
     {
-      uchar4 t = make_uchar4(0, 0, 0, 0);
-      if (p.faceTypes != nullptr && el >= 0) {
-        t = *reinterpret_cast<const uchar4*>(p.faceTypes + 4 * el);
-      }
       const bool none = el < 0;  // FaceType::DynamicRupture (3) gets no local flux
-      skipFace[0] = none || t.x == 3; skipFace[1] = none || t.y == 3;
-      skipFace[2] = none || t.z == 3; skipFace[3] = none || t.w == 3;
+      skipFace[0] = none || ft.x == 3; skipFace[1] = none || ft.y == 3;
+      skipFace[2] = none || ft.z == 3; skipFace[3] = none || ft.w == 3;
     }
 
     mbar_wait(bar, phase);
@@ -376,9 +381,14 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
     __syncthreads();
 
     // ---- local flux: update += rDivM_f . ((fMrT_f . I) . AplusT_f), skipped on DR faces
-    R sNext[3][3];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
+      if (f == 2) {
+        nextMy = (haveNext && le >= 0) ? elemOf(nextBatch, le) : -1;
+        nextEl = (haveNext && active) ? elemOf(nextBatch, g) : -1;
+        nextLI = nextEl >= 0 ? static_cast<const R*>(p.localInt.at(nextEl)) : nullptr;
+        ftNext = faceTypesOf(nextEl);
+      }
       R a[kNQ];
       auto loadA = [&]() {
 #pragma unroll
@@ -428,11 +438,12 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
             mbar_arrive_expect_tx(bar, 0);
           }
         }
+        // ... and its star coefficients are pulled into the L2 now and loaded at the bottom of the loop, when the
+        // accumulators are dead (loading them here spilled them to local memory behind a full-latency stall)
+        if (nextLI != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            sNext[j][c] = (nextLI != nullptr && c < kStarCnt[q]) ? nextLI[24 * j + kStarOff[q] + c] : R(0);
+          for (int j = 0; j < 3; ++j) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nextLI + 24 * j + sOff));
           }
         }
       }
@@ -459,12 +470,13 @@ __global__ void __launch_bounds__(blockThreads(E), SSB_MINB_LOCAL5) k_local5(con
     myElem = nextMy;
     el = nextEl;
     LI = nextLI;
+    ft = ftNext;
     if (haveNext) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          s[j][c] = sNext[j][c];
+          s[j][c] = (LI != nullptr && c < sCnt) ? LI[24 * j + sOff + c] : R(0);
         }
       }
     }

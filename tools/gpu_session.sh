@@ -150,6 +150,14 @@ drtc2)
   SSB_DR_TC=1 timeout 300 python tools/quick_bench_dr.py > $out/qbdr_tc.txt 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_dr_interp_tc' --launch-skip 2 -c 1 -f -o $out/full_drtc \
       env SSB_DR_TC=1 python tools/quick_bench_dr.py --steps 1 > $out/ncu_drtc.log 2>&1 ;;
+nfvar)
+  for v in nf14 nf16 nf10; do
+    L=$PWD/seissol_b200/lib/libseissol_b200_$v.so
+    [ -f $L ] && SSB_LIB=$L timeout 300 python tools/quick_bench.py --kernels neigh,all > $out/qb_$v.txt 2>&1
+  done
+  timeout 300 python tools/quick_bench.py --kernels neigh,all > $out/qb_base.txt 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_local5|k_neigh_fp' --launch-skip 2 -c 2 -f -o $out/full_l5 \
+      python tools/quick_bench.py --cells 296000 --steps 1 --kernels all > $out/ncu_l5.log 2>&1 ;;
 umma)
   timeout 60 tools/ubench/umma_test > $out/umma_test.txt 2>&1; echo "exit $?" >> $out/umma_test.txt
   timeout 120 tools/ubench/fma_peak > $out/fma_peak.txt 2>&1 ;;
