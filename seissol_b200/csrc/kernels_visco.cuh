@@ -41,6 +41,9 @@ __device__ constexpr int kVStarRow[15][3] = {{6, 7, 8}, {6, 7, 8}, {6, 7, 8}, {6
 __device__ constexpr int kVStarCnt[15] = {3, 3, 3, 2, 2, 2, 3, 3, 3, 1, 1, 1, 2, 2, 2};
 __device__ constexpr int kVStarOff[15] = {0, 3, 6, 9, 11, 13, 15, 18, 21, 24, 25, 26, 27, 29, 31};
 
+#ifndef SSB_VISCO_MINB
+#define SSB_VISCO_MINB 2   // resident CTAs per SM the register allocation is sized for
+#endif
 template <typename R, typename G, int E>
 struct ViscoPlan {
   static constexpr int BP = G::kBP;
@@ -95,7 +98,7 @@ __device__ __forceinline__ void viscoStar(R (&s)[3][3], const R* li, int q) {
 
 // ---------------------------------------------------------------------------------------
 template <typename R, typename G, int E>
-__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_ader(const ViscoLocalParams p) {
+__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), SSB_VISCO_MINB) k_visco_ader(const ViscoLocalParams p) {
   using P = ViscoPlan<R, G, E>;
   constexpr int BP = P::BP, TQ = P::TQ, TA = P::TA, O = G::kOrder;
   constexpr int R1 = pad4i(G::derRows(1));  // rows of dQext(d): kDivMT lowers the polynomial degree
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_ader
 
 // ---------------------------------------------------------------------------------------
 template <typename R, typename G, int E>
-__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_local(const ViscoLocalParams p) {
+__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), SSB_VISCO_MINB) k_visco_local(const ViscoLocalParams p) {
   using P = ViscoPlan<R, G, E>;
   constexpr int BP = P::BP, B2P = P::B2P, TQ = P::TQ, TA = P::TA, TF = P::TF;
   extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_loca
 
 // ---------------------------------------------------------------------------------------
 template <typename R, typename G, int E>
-__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), 2) k_visco_neigh(const ViscoNeighParams p) {
+__global__ void __launch_bounds__((ViscoPlan<R, G, E>::threads), SSB_VISCO_MINB) k_visco_neigh(const ViscoNeighParams p) {
   using P = ViscoPlan<R, G, E>;
   constexpr int BP = P::BP, B2P = P::B2P, TQ = P::TQ, TF = P::TF;
   extern __shared__ __align__(128) unsigned char smemRaw[];
