@@ -183,6 +183,14 @@ typedef struct ssb_friction_data {
   void* initial_pressure;                             /* InitialPressure [n][ppad] */
   const void* nucleation_stress;                      /* NucleationStressInFaultCS [n][nucleation_count][6][ppad] */
   const void* nucleation_pressure;                    /* NucleationPressure [n][nucleation_count][ppad] */
+  /* friction energy output (drParameters.isFrictionEnergyRequired; all NULL = off): common::computeFrictionEnergy
+   * (FrictionSolverCommon.h:632-722, called at the end of BaseFrictionLaw::evaluate :173-182) accumulates DREnergyOutput
+   * (src/Initializer/Typedefs.h:237-241) from the interpolated fields of the step. */
+  void* energy_slip;                                  /* DREnergyOutput::slip [n][3][ppad], in/out */
+  void* energy_accumulated_slip;                      /* DREnergyOutput::accumulatedSlip [n][ppad], in/out */
+  void* frictional_energy;                            /* DREnergyOutput::frictionalEnergy [n][ppad], in/out */
+  const void* space_weights;                          /* [P] quadrature weights of the fault points */
+  const void* doubled_surface_area;                   /* [n] DRGodunovData::doubledSurfaceArea */
 } ssb_friction_data_t;
 
 /* Scalars of FrictionSolver::evaluate and FrictionLawParameters (DynamicRupture/Misc.h:254-287). */
@@ -199,7 +207,7 @@ typedef struct ssb_friction_params {
   int rs_max_number_slip_rate_updates;
   int rs_number_state_variable_updates;
   int nucleation_count;    /* drParameters.nucleationCount (<= 4); 0 = no nucleation */
-  int reserved;
+  int energies_from_across_fault_velocities;  /* drParameters.energiesFromAcrossFaultVelocities (friction energy output) */
   double nucleation_t0[4]; /* drParameters.t0[i]: effective rise time of nucleation i (t0[0] is also `t0` above) */
   double nucleation_s0[4]; /* drParameters.s0[i]: onset time of nucleation i */
 } ssb_friction_params_t;

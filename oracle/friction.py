@@ -389,9 +389,35 @@ COMMON_STATE = ["mu", "slip1", "slip2", "slipRate1", "slipRate2", "slipRateMagni
 COMMON_FLAGS = ["ruptureTimePending", "dynStressTimePending"]
 
 
-def evaluate(law, st, imp, qip, qim, full_update_time, dts, time_weights):
+def compute_friction_energy(energy, f, imp, qip_f, qim_f, time_weights, slip_rate_magnitude_f):
+    """common::computeFrictionEnergy (FrictionSolverCommon.h:632-722) for face f.  energy: dict(slip [nF, 3, P],
+    accumulatedSlip [nF, P], frictionalEnergy [nF, P], spaceWeights [P], doubledSurfaceArea [nF],
+    fromAcrossFaultVelocities bool), accumulated in place."""
+    dt = qip_f.dtype.type
+    b_plus = imp["etaS"][f] * imp["invZs"][f]
+    b_minus = imp["etaS"][f] * imp["invZsNeig"][f]
+    area_n = -dt(energy["doubledSurfaceArea"][f])
+    for o in range(qip_f.shape[0]):
+        w = dt(time_weights[o])
+        d1 = qim_f[o, :, U_] - qip_f[o, :, U_]
+        d2 = qim_f[o, :, V_] - qip_f[o, :, V_]
+        d3 = qim_f[o, :, W_] - qip_f[o, :, W_]
+        if energy["fromAcrossFaultVelocities"]:
+            energy["accumulatedSlip"][f] += w * np.sqrt(d1 * d1 + d2 * d2 + d3 * d3)
+        else:
+            energy["accumulatedSlip"][f] += w * slip_rate_magnitude_f
+        energy["slip"][f, 0] += w * d1
+        energy["slip"][f, 1] += w * d2
+        energy["slip"][f, 2] += w * d3
+        t12 = b_plus * qim_f[o, :, T1_] + b_minus * qip_f[o, :, T1_]
+        t13 = b_plus * qim_f[o, :, T2_] + b_minus * qip_f[o, :, T2_]
+        energy["frictionalEnergy"][f] += (w * energy["spaceWeights"].astype(qip_f.dtype) * area_n) * (t12 * d2 + t13 * d3)
+
+
+def evaluate(law, st, imp, qip, qim, full_update_time, dts, time_weights, energy=None):
     """BaseFrictionLaw<D>::evaluate (CpuImpl/BaseFrictionLaw.h:49-189) over all faces.
-    st: dict of state arrays (updated in place); qip/qim: [nF, O, P, 9].
+    st: dict of state arrays (updated in place); qip/qim: [nF, O, P, 9]; energy: optional friction energy output
+    (compute_friction_energy, drParameters.isFrictionEnergyRequired).
     Returns imposedStatePlus, imposedStateMinus: [nF, P, 9]."""
     nf, order, P, _ = qip.shape
     dt = qip.dtype.type
@@ -418,6 +444,8 @@ def evaluate(law, st, imp, qip, qim, full_update_time, dts, time_weights):
             st["peakSlipRate"][f] = np.maximum(st["peakSlipRate"][f], st["slipRateMagnitude"][f])
         law.post_hook(st, f, state_buf)
         plus[f], minus[f] = postcompute_imposed(imp, f, ns, tr1, tr2, qip[f], qim[f], time_weights)
+        if energy is not None:
+            compute_friction_energy(energy, f, imp, qip[f], qim[f], time_weights, st["slipRateMagnitude"][f])
     return plus, minus
 
 

@@ -34,7 +34,8 @@ FRICTION_DATA_FIELDS = [
     "rupture_time_pending", "dyn_stress_time_pending",
     "d_c", "mu_s", "mu_d", "cohesion", "forced_rupture_time",
     "rs_a", "rs_sl0", "rs_f0", "rs_mu_w", "rs_b", "rs_sr_w", "state_variable", "convergence_inner",
-    "convergence_outer", "resample_t", "initial_pressure", "nucleation_stress", "nucleation_pressure"]
+    "convergence_outer", "resample_t", "initial_pressure", "nucleation_stress", "nucleation_pressure",
+    "energy_slip", "energy_accumulated_slip", "frictional_energy", "space_weights", "doubled_surface_area"]
 
 
 class SsbFrictionData(ctypes.Structure):
@@ -49,7 +50,7 @@ class SsbFrictionParams(ctypes.Structure):
                 ("healing_threshold", ctypes.c_double), ("t0", ctypes.c_double), ("rs_sr0", ctypes.c_double),
                 ("rs_slip_rate_tolerance", ctypes.c_double), ("rs_state_tolerance", ctypes.c_double),
                 ("rs_max_number_slip_rate_updates", ctypes.c_int), ("rs_number_state_variable_updates", ctypes.c_int),
-                ("nucleation_count", ctypes.c_int), ("reserved", ctypes.c_int),
+                ("nucleation_count", ctypes.c_int), ("energies_from_across_fault_velocities", ctypes.c_int),
                 ("nucleation_t0", ctypes.c_double * 4), ("nucleation_s0", ctypes.c_double * 4)]
 
 

@@ -597,6 +597,14 @@ int friction(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params
   p.initialPressure = d->initial_pressure;
   p.nucleationStress = d->nucleation_stress;
   p.nucleationPressure = d->nucleation_pressure;
+  p.energySlip = d->energy_slip; p.energyAccumulatedSlip = d->energy_accumulated_slip;
+  p.frictionalEnergy = d->frictional_energy; p.spaceWeights = d->space_weights;
+  p.doubledSurfaceArea = d->doubled_surface_area;
+  p.energiesFromAcrossFaultVelocities = q->energies_from_across_fault_velocities;
+  if (p.frictionalEnergy != nullptr && (p.energySlip == nullptr || p.energyAccumulatedSlip == nullptr ||
+                                        p.spaceWeights == nullptr || p.doubledSurfaceArea == nullptr)) {
+    return SSB_EINVAL;   // the energy output needs all of its arrays
+  }
   p.nucleationCount = q->nucleation_count;
   if (p.nucleationCount < 0 || p.nucleationCount > 4 || (p.nucleationCount > 0 && p.nucleationStress == nullptr)) {
     return SSB_EINVAL;

@@ -529,6 +529,29 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
     ip[c * p.ppad] = valsP[c];
     im[c * p.ppad] = valsM[c];
   }
+  // ---- common::computeFrictionEnergy (FrictionSolverCommon.h:632-722), from the interpolated fields still in registers
+  if (p.frictionalEnergy != nullptr) {
+    const R bPlus = etaS * invZs, bMinus = etaS * invZsNeig;
+    const R areaN = -static_cast<const R*>(p.doubledSurfaceArea)[face];
+    const R spaceW = static_cast<const R*>(p.spaceWeights)[pt];
+    R* const eSlip = static_cast<R*>(p.energySlip) + face * 3 * p.ppad + pt;
+    R eAcc = fp.template get<R>(p.energyAccumulatedSlip);
+    R eFric = fp.template get<R>(p.frictionalEnergy);
+    R e1 = eSlip[0], e2 = eSlip[p.ppad], e3 = eSlip[2 * p.ppad];
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      const R w = static_cast<R>(p.timeWeights[o]);
+      const R d1 = qmU[o] - qpU[o], d2 = qmV[o] - qpV[o], d3 = qmW[o] - qpW[o];
+      eAcc += w * (p.energiesFromAcrossFaultVelocities ? sqrt(d1 * d1 + d2 * d2 + d3 * d3) : srm);
+      e1 += w * d1; e2 += w * d2; e3 += w * d3;
+      const R t12 = bPlus * qmT1[o] + bMinus * qpT1[o];
+      const R t13 = bPlus * qmT2[o] + bMinus * qpT2[o];
+      eFric += (w * spaceW * areaN) * (t12 * d2 + t13 * d3);
+    }
+    eSlip[0] = e1; eSlip[p.ppad] = e2; eSlip[2 * p.ppad] = e3;
+    fp.template at<R>(p.energyAccumulatedSlip) = eAcc;
+    fp.template at<R>(p.frictionalEnergy) = eFric;
+  }
   if (nuc > 0) {
     stress[0] = s0; stress[1 * p.ppad] = s1; stress[2 * p.ppad] = s2;
     stress[3 * p.ppad] = s3; stress[4 * p.ppad] = s4; stress[5 * p.ppad] = s5;

@@ -117,6 +117,13 @@ struct FrictionParams {
   int nucleationCount;
   double nucleationT0[4];
   double nucleationS0[4];
+  // friction energy output (common::computeFrictionEnergy); frictionalEnergy == null: off
+  void* energySlip;                 // [n][3][ppad]
+  void* energyAccumulatedSlip;      // [n][ppad]
+  void* frictionalEnergy;           // [n][ppad]
+  const void* spaceWeights;         // [P]
+  const void* doubledSurfaceArea;   // [n]
+  int energiesFromAcrossFaultVelocities;
 };
 
 struct NeighDrParams {

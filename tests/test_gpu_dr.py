@@ -185,6 +185,53 @@ def test_friction_laws(gpu, law, order, dt, nucleation):
             assert np.array_equal(d["convergence_outer"].cpu().numpy()[:, :P].astype(bool), st["convergenceOuter"])
 
 
+@pytest.mark.parametrize("law", ["lsw", "rsfvw"])
+@pytest.mark.parametrize("dt,from_velocities", [(np.float64, True), (np.float64, False), (np.float32, True)])
+def test_friction_energy_output(gpu, law, dt, from_velocities):
+    """DREnergyOutput (slip, accumulated slip, frictional energy) accumulated by the friction kernels over two steps
+    (common::computeFrictionEnergy, FrictionSolverCommon.h:632-722) against the oracle."""
+    torch, api, proxy = gpu
+    order, nf = 6, 23
+    ctx = api.Context(order, np.dtype(dt).itemsize)
+    tab = O.load_tables(order, dt)
+    P = (order + 1) ** 2
+    st, imp, params = F.fault_state(law, nf, order, dt)
+    qip, qim = F.fault_qinterpolated(nf, order, dt)
+    rng = np.random.default_rng(4)
+    d, names = _friction_device_data(torch, ctx, proxy, st, imp, qip, qim, tab["resample"], law)
+    dev = torch.device("cuda")
+    area = rng.uniform(1.0, 3.0, nf).astype(dt)
+    sw = tab["quadweights"].astype(dt)
+    d["energy_slip"] = torch.zeros((nf, 3, ctx.ppad), device=dev, dtype=d["mu"].dtype)
+    d["energy_accumulated_slip"] = torch.zeros((nf, ctx.ppad), device=dev, dtype=d["mu"].dtype)
+    d["frictional_energy"] = torch.zeros((nf, ctx.ppad), device=dev, dtype=d["mu"].dtype)
+    d["space_weights"] = torch.from_numpy(sw).to(dev)
+    d["doubled_surface_area"] = torch.from_numpy(area).to(dev)
+    lawobj = (F.LinearSlipWeakening if law == "lsw" else F.RateAndStateFastVelocityWeakening)(params, tab["resample"])
+    if law == "rsfvw" and dt == np.float32:   # as test_friction_laws: the double-precision oracle on the float inputs
+        up = lambda x: x.astype(np.float64) if isinstance(x, np.ndarray) and x.dtype == np.float32 else x  # noqa: E731
+        st, imp, qip, qim = {k: up(v) for k, v in st.items()}, {k: up(v) for k, v in imp.items()}, up(qip), up(qim)
+        lawobj = F.RateAndStateFastVelocityWeakening(params, tab["resample"].astype(np.float64))
+    odt = qip.dtype
+    energy = {"slip": np.zeros((nf, 3, P), dtype=odt), "accumulatedSlip": np.zeros((nf, P), dtype=odt),
+              "frictionalEnergy": np.zeros((nf, P), dtype=odt), "spaceWeights": sw.astype(odt),
+              "doubledSurfaceArea": area.astype(odt), "fromAcrossFaultVelocities": from_velocities}
+    step = 1e-3
+    for s_ in range(2):
+        fp, dts, wts = proxy.friction_params(order, step, full_update_time=0.25 + s_ * step, rs_sr0=params.rsSr0,
+                                             healing_threshold=params.healingThreshold, t0=params.t0,
+                                             energies_from_across_fault_velocities=from_velocities)
+        ctx.friction(law, d, fp, nf)
+        F.evaluate(lawobj, st, imp, qip, qim, 0.25 + s_ * step, dts, wts, energy=energy)
+    torch.cuda.synchronize()
+    t = 1e-11 if dt == np.float64 and law == "lsw" else (1e-7 if dt == np.float64 else (2e-5 if law == "lsw" else 2e-2))
+    got_slip = d["energy_slip"].cpu().numpy()[:, :, :P]
+    assert rel_l2(got_slip, energy["slip"]) < t
+    assert rel_l2(d["energy_accumulated_slip"].cpu().numpy()[:, :P], energy["accumulatedSlip"]) < t
+    assert rel_l2(d["frictional_energy"].cpu().numpy()[:, :P], energy["frictionalEnergy"]) < t
+    assert np.abs(energy["frictionalEnergy"]).max() > 0
+
+
 @pytest.mark.parametrize("order,dt", [(4, np.float32), (6, np.float32), (6, np.float64)])
 def test_neigh_dr_nodal_flux(gpu, order, dt):
     torch, api, proxy = gpu

@@ -166,3 +166,37 @@ def test_adjust_initial_stress_ramps_to_the_nucleation_stress():
     assert np.allclose(st["initialStress"][0], st["nucleationStress"][0].sum(0), atol=5e-3)
     assert np.allclose(st["initialPressure"][0], st["nucleationPressure"][0].sum(0), atol=5e-3)
     assert np.abs(st["initialStress"][0]).max() > 0.5
+
+
+def test_friction_energy_closed_form():
+    """common::computeFrictionEnergy (FrictionSolverCommon.h:632-722) on a constant slip-rate field: the slip grows by
+    the across-fault velocity x dt, the accumulated slip by its magnitude, the frictional energy by
+    -area x space weight x (traction . slip rate) x dt (the closed form of the reference's definition)."""
+    dt_ = np.float64
+    nf, order, P = 2, 4, 25
+    st, imp, params = F.fault_state("lsw", nf, order, dt_)
+    qip = np.zeros((nf, order, P, 9))
+    qim = np.zeros((nf, order, P, 9))
+    qim[..., F.U_], qim[..., F.V_], qim[..., F.W_] = 0.5, 2.0, -1.0     # constant velocity jump
+    qip[..., F.T1_], qim[..., F.T1_] = 3e6, 1e6
+    qip[..., F.T2_], qim[..., F.T2_] = -2e6, 4e6
+    step = 1e-3
+    _, w = O.gauss_legendre_shifted(order, 0.0, step)
+    sw = np.linspace(0.5, 1.5, P)
+    energy = {"slip": np.zeros((nf, 3, P)), "accumulatedSlip": np.zeros((nf, P)), "frictionalEnergy": np.zeros((nf, P)),
+              "spaceWeights": sw, "doubledSurfaceArea": np.array([2.0, 3.0]), "fromAcrossFaultVelocities": True}
+    for f in range(nf):
+        F.compute_friction_energy(energy, f, imp, qip[f], qim[f], w, st["slipRateMagnitude"][f])
+    assert np.allclose(energy["slip"][:, 0], 0.5 * step) and np.allclose(energy["slip"][:, 1], 2.0 * step)
+    assert np.allclose(energy["accumulatedSlip"], np.sqrt(0.25 + 4 + 1) * step)
+    for f in range(nf):
+        bp, bm = imp["etaS"][f] * imp["invZs"][f], imp["etaS"][f] * imp["invZsNeig"][f]
+        t12, t13 = bp * 1e6 + bm * 3e6, bp * 4e6 + bm * (-2e6)
+        want = -energy["doubledSurfaceArea"][f] * sw * (t12 * 2.0 + t13 * (-1.0)) * step
+        assert np.allclose(energy["frictionalEnergy"][f], want, rtol=1e-12)
+    # the other definition of the accumulated slip: the friction law's slip-rate magnitude
+    energy2 = dict(energy, accumulatedSlip=np.zeros((nf, P)), slip=np.zeros((nf, 3, P)), frictionalEnergy=np.zeros((nf, P)),
+                   fromAcrossFaultVelocities=False)
+    st["slipRateMagnitude"][:] = 0.25
+    F.compute_friction_energy(energy2, 0, imp, qip[0], qim[0], w, st["slipRateMagnitude"][0])
+    assert np.allclose(energy2["accumulatedSlip"][0], 0.25 * step)
