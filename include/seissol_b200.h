@@ -258,6 +258,28 @@ int ssb_visco_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb
                        const void* const* godunov, const void* const* flux_solver, const uint8_t* side_rel,
                        const uint8_t* face_types, long long n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Set-up on the device (elastic): the per-element and per-fault-face matrices the entry points above consume, from
+ * vertex coordinates and material parameters; all inputs are DEVICE arrays of doubles, results are stored in the
+ * precision of the context.
+ * ssb_setup_cell_matrices replaces initializeCellLocalMatrices (src/Initializer/Model/CellLocalMatrices.cpp:66-298) for
+ * the elastic model: local_int = star[3][24] | nApNm1[4][81], neigh_int = nAmNm1[4][81].  coords [n][4][3];
+ * neighbors [n][4]: row of `material` of the face neighbor (< 0: none, the own material is used); material [*][3] =
+ * lambda, mu, rho (rows 0..n-1 = own cells, further rows = ghost cells); face_types [n][4] or NULL: FreeSurface (1) gets
+ * the free-surface Godunov state (src/Model/Common.h:319-364), DynamicRupture (3) no local flux matrix.
+ * ssb_setup_dr_matrices replaces the matrix part of initializeDynamicRuptureMatrices
+ * (src/Initializer/Model/DynamicRuptureMatrices.cpp:111-477: impedances and eta :341-359, TinvT :427, flux solvers
+ * :461-469): coords_plus / coords_minus [m][4][3] of the two elements of every fault face, face_info [m][3] = {plusSide,
+ * minusSide, faceRelation}, material_plus / minus [m][3]; out: tinv_t [m][81], imp_and_eta [m][11], flux_solver_plus /
+ * minus [m][81] (column-major [c + 9 q]), doubled_surface_area [m] (may be NULL). */
+int ssb_setup_cell_matrices(ssb_ctx* ctx, const double* coords, const long long* neighbors, const double* material,
+                            const uint8_t* face_types, ssb_array_t local_int, ssb_array_t neigh_int, long long n,
+                            void* stream);
+int ssb_setup_dr_matrices(ssb_ctx* ctx, const double* coords_plus, const double* coords_minus, const uint8_t* face_info,
+                          const double* material_plus, const double* material_minus, void* tinv_t, void* imp_and_eta,
+                          void* flux_solver_plus, void* flux_solver_minus, void* doubled_surface_area, long long m,
+                          void* stream);
+
 const char* ssb_error_string(int code);
 const char* ssb_version(void);
 

@@ -19,6 +19,7 @@ SYMBOLS = [
     "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj", "ssb_taylor_faceproj", "ssb_accumulate_rows",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh", "ssb_visco_neigh_dr",
+    "ssb_setup_cell_matrices", "ssb_setup_dr_matrices",
     "ssb_error_string", "ssb_version",
 ]
 
@@ -98,6 +99,8 @@ def load_library():
     lib.ssb_visco_local.argtypes = [P, A, A, A, A, A, P, LL, P]
     lib.ssb_visco_neigh.argtypes = [P, A, A, P, P, A, A, P, P, LL, P, P]
     lib.ssb_visco_neigh_dr.argtypes = [P, A, A, A, P, P, P, P, LL, P]
+    lib.ssb_setup_cell_matrices.argtypes = [P, P, P, P, P, A, A, LL, P]
+    lib.ssb_setup_dr_matrices.argtypes = [P, P, P, P, P, P, P, P, P, P, P, LL, P]
     _lib = lib
     return lib
 
@@ -250,6 +253,19 @@ class Context:
     def visco_neigh_dr(self, dofs, dofs_ane, neigh_int, godunov_ptrs, flux_solver_ptrs, side_rel, face_types, n, stream=None):
         _check(self.lib.ssb_visco_neigh_dr(self.handle, dofs, dofs_ane, neigh_int, _ptr(godunov_ptrs), _ptr(flux_solver_ptrs),
                                            _ptr(side_rel), _ptr(face_types), n, _stream(stream)))
+
+    # -- set-up on the device --------------------------------------------------------------------
+    def setup_cell_matrices(self, coords, neighbors, material, face_types, local_int, neigh_int, n, stream=None):
+        """coords [n, 4, 3] f64, neighbors [n, 4] i64, material [*, 3] f64 (device tensors) -> local_int, neigh_int."""
+        _check(self.lib.ssb_setup_cell_matrices(self.handle, _ptr(coords), _ptr(neighbors), _ptr(material), _ptr(face_types),
+                                                local_int, neigh_int, n, _stream(stream)))
+
+    def setup_dr_matrices(self, coords_plus, coords_minus, face_info, material_plus, material_minus, tinv_t, imp_and_eta,
+                          flux_solver_plus, flux_solver_minus, doubled_surface_area, m, stream=None):
+        _check(self.lib.ssb_setup_dr_matrices(self.handle, _ptr(coords_plus), _ptr(coords_minus), _ptr(face_info),
+                                              _ptr(material_plus), _ptr(material_minus), _ptr(tinv_t), _ptr(imp_and_eta),
+                                              _ptr(flux_solver_plus), _ptr(flux_solver_minus), _ptr(doubled_surface_area), m,
+                                              _stream(stream)))
 
     # -- dynamic rupture ------------------------------------------------------------------------
     def dr_interp(self, der_plus, der_minus, tinv_t, face_info, q_plus, q_minus, coeffs, n, perm=None, stream=None):

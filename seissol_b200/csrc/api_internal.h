@@ -78,6 +78,11 @@ struct KernelSet {
   int (*taylorFp)(const TaylorParams&, cudaStream_t);   // Taylor sum + face projection (full-column units only)
 };
 
+struct SetupCellParams;
+struct SetupDrParams;
+int setupCellEntry(const SetupCellParams&, int realSize, cudaStream_t);
+int setupDrEntry(const SetupDrParams&, int realSize, cudaStream_t);
+
 struct DrKernelSet {
   int order;
   int realSize;

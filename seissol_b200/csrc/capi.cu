@@ -8,6 +8,7 @@
 
 #include "../../include/seissol_b200.h"
 #include "api_internal.h"
+#include "kernels_setup.cuh"
 
 using namespace ssb;
 
@@ -793,6 +794,50 @@ int ssb_visco_neigh_dr(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_a
   p.ldg = c->ldq;
   p.ppad = c->ppad;
   return c->visco->neighDr(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_setup_cell_matrices(ssb_ctx* c, const double* coords, const long long* neighbors, const double* material,
+                            const uint8_t* face_types, ssb_array_t local_int, ssb_array_t neigh_int, long long n, void* stream) {
+  if (c == nullptr || n < 0 || c->equation != 0) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  SetupCellParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.coords = coords; p.neighbors = neighbors; p.material = material; p.faceTypes = face_types;
+  p.localInt = conv(local_int); p.neighInt = conv(neigh_int);
+  p.n = n;
+  if (coords == nullptr || neighbors == nullptr || material == nullptr || !p.localInt.present() || !p.neighInt.present()) {
+    return SSB_EINVAL;
+  }
+  return setupCellEntry(p, c->realSize, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_setup_dr_matrices(ssb_ctx* c, const double* coords_plus, const double* coords_minus, const uint8_t* face_info,
+                          const double* material_plus, const double* material_minus, void* tinv_t, void* imp_and_eta,
+                          void* flux_solver_plus, void* flux_solver_minus, void* doubled_surface_area, long long m,
+                          void* stream) {
+  if (c == nullptr || m < 0 || c->equation != 0) {
+    return SSB_EINVAL;
+  }
+  if (m == 0) {
+    return 0;
+  }
+  if (coords_plus == nullptr || coords_minus == nullptr || face_info == nullptr || material_plus == nullptr ||
+      material_minus == nullptr || tinv_t == nullptr || imp_and_eta == nullptr || flux_solver_plus == nullptr ||
+      flux_solver_minus == nullptr) {
+    return SSB_EINVAL;
+  }
+  SetupDrParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.coordsPlus = coords_plus; p.coordsMinus = coords_minus; p.faceInfo = face_info;
+  p.materialPlus = material_plus; p.materialMinus = material_minus;
+  p.tinvT = tinv_t; p.impAndEta = imp_and_eta; p.fluxSolverPlus = flux_solver_plus; p.fluxSolverMinus = flux_solver_minus;
+  p.doubledSurfaceArea = doubled_surface_area;
+  p.m = m;
+  return setupDrEntry(p, c->realSize, static_cast<cudaStream_t>(stream));
 }
 
 const char* ssb_error_string(int code) {

@@ -126,6 +126,46 @@ def cell_local_matrices(coords, neighbors, lam, mu, rho, star_pattern, face_type
     return star, aplus, aminus
 
 
+def face_frame(c, f):
+    """Unit normal and tangents, area of face f and volume of the tetrahedron c [4, 3] (MeshTools.cpp:44-132)."""
+    a, b, cc = c[FACE2NODES[f]]
+    normal = np.cross(b - a, cc - a)
+    t1 = b - a
+    t2 = np.cross(normal, t1)
+    volume = abs(np.linalg.det(c[1:] - c[:1])) / 6.0
+    return (normal / np.linalg.norm(normal), t1 / np.linalg.norm(t1), t2 / np.linalg.norm(t2),
+            0.5 * np.linalg.norm(normal), volume)
+
+
+def dr_matrices(coords_plus, coords_minus, face_info, mat_plus, mat_minus):
+    """Fault-face matrices (host restatement of src/Initializer/Model/DynamicRuptureMatrices.cpp:111-477): impedances and
+    eta (:341-359), TinvT (:427), fluxSolverPlus / Minus = fluxScale star0 . T^T (:461-469, dynamic_rupture.py:88),
+    doubledSurfaceArea.  coords_* [m, 4, 3], face_info [m, 3] = {plusSide, minusSide, faceRelation}, mat_* [m, 3] =
+    lambda, mu, rho.  Returns tinvT [m, 9, 9], imp_and_eta [m, 11], fs_plus, fs_minus [m, 9, 9] (row = quantity of the
+    imposed state, column = updated quantity), doubled_area [m]."""
+    m = coords_plus.shape[0]
+    tinv_t = np.zeros((m, 9, 9))
+    imp = np.zeros((m, 11))
+    fsp = np.zeros((m, 9, 9))
+    fsm = np.zeros((m, 9, 9))
+    area2 = np.zeros(m)
+    for i in range(m):
+        lp, mp, rp = mat_plus[i]
+        lm, mm, rm = mat_minus[i]
+        zp, zs = rp * np.sqrt((lp + 2 * mp) / rp), rp * np.sqrt(mp / rp)
+        zpn, zsn = rm * np.sqrt((lm + 2 * mm) / rm), rm * np.sqrt(mm / rm)
+        imp[i] = [zp, zs, zpn, zsn, 1.0 / (1.0 / zp + 1.0 / zpn), 1.0 / (1.0 / zs + 1.0 / zsn), 1.0 / zs + 1.0 / zsn,
+                  1.0 / zp, 1.0 / zs, 1.0 / zpn, 1.0 / zsn]
+        n, s, t, surf_p, vol_p = face_frame(coords_plus[i], face_info[i, 0])
+        _, _, _, surf_m, vol_m = face_frame(coords_minus[i], face_info[i, 1])
+        T, Ti = rotation_matrices(n, s, t)
+        tinv_t[i] = Ti.T
+        area2[i] = 2.0 * surf_m
+        fsp[i] = (-2.0 * surf_p / (6.0 * vol_p)) * (coefficient_matrix_T(lp, mp, rp, 0) @ T.T)
+        fsm[i] = (2.0 * surf_m / (6.0 * vol_m)) * (coefficient_matrix_T(lm, mm, rm, 0) @ T.T)
+    return tinv_t, imp, fsp, fsm, area2
+
+
 def plane_wave(lam, mu, rho, direction, wavelength_count, length, kind="P"):
     """Exact plane-wave solution Q(x, t) of the homogeneous elastic equations in a periodic box of edge `length`:
     returns (func(x, t) -> [.., 9], wave speed).  direction: integer vector (periodicity), kind 'P' or 'S'."""
