@@ -76,9 +76,11 @@ def cluster_of_x(cube_x, nx, n_clusters):
     return tri[(cube_x // 2) % period]
 
 
-def build_layout(nx, ny, nz, rank, world, n_clusters=1, cluster_axis="z"):
+def build_layout(nx, ny, nz, rank, world, n_clusters=1, cluster_axis="z", cluster_by_gid=None):
     """Layout of `rank`: which cells it owns, in which order, where its ghost cells sit and what is exchanged.
-    cluster_axis: "z" = horizontal bands (remote neighbors share the cluster), "x" = bands across the slabs."""
+    cluster_axis: "z" = horizontal bands (remote neighbors share the cluster), "x" = bands across the slabs;
+    cluster_by_gid: time cluster of every GLOBAL element id (e.g. seissol_b200/clustering.py::best_clustering on the
+    whole mesh: clusters from the cells' CFL time steps), overrides the synthetic bands."""
     if nx % world:
         raise ValueError("nx must be a multiple of the number of ranks")
     nxl = nx // world
@@ -94,7 +96,10 @@ def build_layout(nx, ny, nz, rank, world, n_clusters=1, cluster_axis="z"):
             lo, hi = 0, nx
         mesh = CubeMesh(nx, ny, nz, lo, hi)
         own = (mesh.cube_x >= x_lo) & (mesh.cube_x < x_hi)
-    cluster = cluster_of_z(mesh.cube_z, nz, n_clusters) if cluster_axis == "z" else cluster_of_x(mesh.cube_x, nx, n_clusters)
+    if cluster_by_gid is not None:
+        cluster = np.asarray(cluster_by_gid, dtype=np.int64)[mesh.gid]
+    else:
+        cluster = cluster_of_z(mesh.cube_z, nz, n_clusters) if cluster_axis == "z" else cluster_of_x(mesh.cube_x, nx, n_clusters)
     nb = mesh.neighbors
     has = nb >= 0
     nb_own = np.where(has, own[np.maximum(nb, 0)], True)
