@@ -258,6 +258,21 @@ int ssb_visco_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb
                        const void* const* godunov, const void* const* flux_solver, const uint8_t* side_rel,
                        const uint8_t* face_types, long long n, void* stream);
 
+/* Nodal boundary conditions of the local integral (Local::computeIntegral, src/Kernels/LinearCK/Local.cpp:157-252; batched
+ * :350-455 through DirichletBoundary::evaluateOnDevice): for m boundary faces (cell[i], face[i]) of FaceType kind[i]
+ *   INodal = V3mTo2nFace_f . I . Tinv^T;   Dirichlet (4): INodal(l, a) = sum_b map(a, b, l) INodal(l, b) + const(a, l)
+ *   (createEasiBoundaryGhostCells);   FreeSurfaceGravity (2): INodal(l, 0..2) = 2 p - INodal(l, 0..2), p = -rho g
+ *   displacement(l);   Q += project2nFaceTo3m_f . INodal . AminusT_f (localFluxNodal; neigh_int holds AminusT as for
+ *   ssb_neigh, with the identity in place of Tinv for these faces as the reference sets it up).
+ * Call it after ssb_local (the reference evaluates these faces inside the local integral).  All face arrays are DEVICE
+ * arrays in the precision of the context: tinv [m][9][9] row-major Tinv(p, q); easi_map [m][9][9][B2] (a, b, l) and
+ * easi_const [m][9][B2] (Dirichlet faces; B2 = O(O+1)/2 face nodes); displacement [m][B2] and rho_g [m]
+ * (FreeSurfaceGravity faces).  Faces of any other kind are skipped.  Two boundary faces of one cell are added with
+ * atomic adds (their order is not fixed).  FaceType::Analytical (a user callback per node and time) is not covered. */
+int ssb_local_nodal_bc(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t neigh_int, const long long* cell,
+                       const uint8_t* face, const uint8_t* kind, const void* tinv, const void* easi_map,
+                       const void* easi_const, const void* displacement, const void* rho_g, long long m, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Set-up on the device (elastic): the per-element and per-fault-face matrices the entry points above consume, from
  * vertex coordinates and material parameters; all inputs are DEVICE arrays of doubles, results are stored in the

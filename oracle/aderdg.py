@@ -33,7 +33,7 @@ def load_tables(order, dtype=np.float64):
     t = {k: z[k] for k in z.files}
     t["kDivMT"] = -t["kDivMT"]
     for k in ("kDivM", "kDivMT", "rDivM", "fMrT", "rT", "fP", "V3mTo2n", "V3mTo2nTWDivM",
-              "resample", "quadweights"):
+              "resample", "quadweights", "V3mTo2nFace", "V2nTo2m"):
         t[k] = t[k].astype(dtype)
     return t
 
@@ -200,6 +200,31 @@ def neighbor(tab, Q, Iall, neighbors, Aminus, face_rel, face_types=None,
                 idx = dr["index"][m, i]
                 mat = tab["V3mTo2nTWDivM"][dr["side"][m, i] + 4 * dr["rel"][m, i]]
                 out[m] += np.matmul(mat, np.matmul(dr["godunov"][idx], dr["fluxSolver"][idx]))
+    return out
+
+
+def local_nodal_bc(tab, Q, I, Aminus, bc):
+    """Nodal boundary conditions of the local integral (Local::computeIntegral, src/Kernels/LinearCK/Local.cpp:157-252;
+    batched :350-455), one boundary face after the other:
+      INodal = V3mTo2nFace_f . I . Tinv^T                    (projectToNodalBoundaryRotated, codegen/kernels/nodalbc.py:73-85)
+      FaceType::Dirichlet (4): INodal(l, a) = sum_b map(a, b, l) INodal(l, b) + const(a, l)   (createEasiBoundaryGhostCells :55-60)
+      FaceType::FreeSurfaceGravity (2): INodal(l, 0..2) = 2 p - INodal(l, 0..2), p = -rho g displacement(l)   (Local.cpp:168-199)
+      Q += (rDivM_f . V2nTo2m) . INodal . AminusT_f          (localFluxNodal, codegen/kernels/aderdg.py:336-352)
+    bc: dict(cell [m], face [m], kind [m], tinv [m, 9, 9], easiMap [m, 9, 9, B2], easiConst [m, 9, B2],
+    displacement [m, B2], rhoG [m]); Aminus dense [n, 4, 9, 9] (flux_dense)."""
+    out = Q.copy()
+    for i in range(len(bc["cell"])):
+        c, f = int(bc["cell"][i]), int(bc["face"][i])
+        if bc["kind"][i] not in (2, 4):
+            continue          # Local.cpp:247-250: no boundary condition, no nodal flux
+        nodal = tab["V3mTo2nFace"][f] @ I[c] @ bc["tinv"][i].T
+        if bc["kind"][i] == 4:
+            nodal = np.einsum("abl,lb->la", bc["easiMap"][i], nodal) + bc["easiConst"][i].T
+        elif bc["kind"][i] == 2:
+            p = (-bc["rhoG"][i] * bc["displacement"][i]).astype(Q.dtype)
+            nodal = nodal.copy()
+            nodal[:, :3] = 2 * p[:, None] - nodal[:, :3]
+        out[c] += (tab["rDivM"][f] @ tab["V2nTo2m"]) @ nodal @ Aminus[c, f]
     return out
 
 

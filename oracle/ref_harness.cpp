@@ -406,4 +406,72 @@ void ssref_set_threads(int n) {
   (void)n;
 #endif
 }
+// Nodal boundary conditions of the local integral (Local::computeIntegral, src/Kernels/LinearCK/Local.cpp:157-252) for m
+// boundary faces, one after the other: projectToNodalBoundaryRotated(face) -> boundary condition at the face nodes ->
+// localFluxNodal(face).  kind 4 = FaceType::Dirichlet (createEasiBoundaryGhostCells: INodal(l, a) = sum_b map(a, b, l)
+// INodal(l, b) + const(a, l)), kind 2 = FaceType::FreeSurfaceGravity (:168-199: the three normal stresses become
+// 2 p - sigma with p = -rho g displacement(l)).  Dense inputs: tinv [m][9][9] row-major Tinv(p, q); easiMap
+// [m][9][9][B2] (a, b, l); easiConst [m][9][B2]; displacement [m][B2]; rhoG [m].
+int64_t ssref_nodal_points() { return tensor::INodal::Shape[0]; }
+void ssref_nodal_bc(int64_t m, real* dofs, const real* Iall, const real* nAmNm1, const int64_t* cell, const uint8_t* face,
+                    const uint8_t* kind, const real* tinv, const real* easiMap, const real* easiConst,
+                    const real* displacement, const double* rhoG) {
+  constexpr unsigned B2 = tensor::INodal::Shape[0];
+  for (int64_t i = 0; i < m; ++i) {
+    alignas(64) real inodal[tensor::INodal::size()] = {};
+    alignas(64) real tinvT[tensor::Tinv::size()] = {};
+    auto tv = init::Tinv::view::create(tinvT);
+    for (unsigned p = 0; p < 9; ++p) {
+      for (unsigned q = 0; q < 9; ++q) {
+        tv(p, q) = tinv[81 * i + 9 * p + q];
+      }
+    }
+    kernel::projectToNodalBoundaryRotated pk;
+    for (unsigned f = 0; f < 4; ++f) {
+      pk.V3mTo2nFace(f) = nodal::init::V3mTo2nFace::Values[f];
+    }
+    pk.I = Iall + cell[i] * ISize;
+    pk.INodal = inodal;
+    pk.Tinv = tinvT;
+    pk.execute(face[i]);
+    auto nv = init::INodal::view::create(inodal);
+    if (kind[i] == 4) {
+      alignas(64) real mapT[tensor::easiBoundaryMap::size()] = {};
+      alignas(64) real constT[tensor::easiBoundaryConstant::size()] = {};
+      auto mv = init::easiBoundaryMap::view::create(mapT);
+      auto cv = init::easiBoundaryConstant::view::create(constT);
+      for (unsigned a = 0; a < 9; ++a) {
+        for (unsigned l = 0; l < B2; ++l) {
+          cv(a, l) = easiConst[(i * 9 + a) * B2 + l];
+          for (unsigned b = 0; b < 9; ++b) {
+            mv(a, b, l) = easiMap[((i * 9 + a) * 9 + b) * B2 + l];
+          }
+        }
+      }
+      kernel::createEasiBoundaryGhostCells ek;
+      ek.easiBoundaryMap = mapT;
+      ek.easiBoundaryConstant = constT;
+      ek.easiIdentMap = init::easiIdentMap::Values;
+      ek.INodal = inodal;
+      ek.execute();
+    } else if (kind[i] == 2) {
+      for (unsigned l = 0; l < B2; ++l) {
+        const double pressureAtBnd = -1 * rhoG[i] * displacement[i * B2 + l];
+        nv(l, 0) = 2 * pressureAtBnd - nv(l, 0);
+        nv(l, 1) = 2 * pressureAtBnd - nv(l, 1);
+        nv(l, 2) = 2 * pressureAtBnd - nv(l, 2);
+      }
+    }
+    kernel::localFluxNodal lf;
+    for (unsigned f = 0; f < 4; ++f) {
+      lf.project2nFaceTo3m(f) = init::project2nFaceTo3m::Values[f];
+    }
+    lf.INodal = inodal;
+    lf.AminusT = nAmNm1 + cell[i] * 324 + 81 * face[i];
+    lf.Q = dofs + cell[i] * QSize;
+    lf._prefetch.I = pk.I;
+    lf._prefetch.Q = lf.Q;
+    lf.execute(face[i]);
+  }
+}
 }

@@ -127,6 +127,19 @@ class RefLib:
                              *[_p(x) for x in args])
         return self.from_ref(q)
 
+    def nodal_bc(self, Q, I, Aminus, bc):
+        """ssref_nodal_bc: the reference's generated projectToNodalBoundaryRotated / createEasiBoundaryGhostCells /
+        localFluxNodal kernels on the boundary faces of `bc` (oracle.aderdg.local_nodal_bc)."""
+        q, i = self.to_ref(Q), self.to_ref(I)
+        m = len(bc["cell"])
+        c = lambda x: np.ascontiguousarray(x, dtype=self.dtype)  # noqa: E731
+        self.lib.ssref_nodal_bc(ctypes.c_int64(m), _p(q), _p(i), _p(c(Aminus)), _p(np.ascontiguousarray(bc["cell"], dtype=np.int64)),
+                                _p(np.ascontiguousarray(bc["face"], dtype=np.uint8)),
+                                _p(np.ascontiguousarray(bc["kind"], dtype=np.uint8)), _p(c(bc["tinv"])), _p(c(bc["easiMap"])),
+                                _p(c(bc["easiConst"])), _p(c(bc["displacement"])),
+                                _p(np.ascontiguousarray(bc["rhoG"], dtype=np.float64)))
+        return self.from_ref(q)
+
     def points_to_ref(self, x):
         """[m, P, 9] -> [m, 9*Ppad] (point fastest)."""
         m, P, _ = x.shape

@@ -76,8 +76,10 @@ struct KernelSet {
   int (*taylor)(const TaylorParams&, cudaStream_t);
   int (*accumulate)(const AccumulateParams&, cudaStream_t);
   int (*taylorFp)(const TaylorParams&, cudaStream_t);   // Taylor sum + face projection (full-column units only)
+  int (*nodalBc)(const struct NodalBcParams&, cudaStream_t);   // nodal boundary conditions (full-column units only)
 };
 
+struct NodalBcParams;
 struct SetupCellParams;
 struct SetupDrParams;
 int setupCellEntry(const SetupCellParams&, int realSize, cudaStream_t);

@@ -9,6 +9,7 @@
 #include "../../include/seissol_b200.h"
 #include "api_internal.h"
 #include "kernels_setup.cuh"
+#include "kernels_nodal.cuh"
 
 using namespace ssb;
 
@@ -794,6 +795,29 @@ int ssb_visco_neigh_dr(ssb_ctx* c, ssb_array_t dofs, ssb_array_t dofs_ane, ssb_a
   p.ldg = c->ldq;
   p.ppad = c->ppad;
   return c->visco->neighDr(p, static_cast<cudaStream_t>(stream));
+}
+
+int ssb_local_nodal_bc(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t neigh_int, const long long* cell,
+                       const uint8_t* face, const uint8_t* kind, const void* tinv, const void* easi_map,
+                       const void* easi_const, const void* displacement, const void* rho_g, long long m, void* stream) {
+  if (c == nullptr || m < 0 || c->equation != 0 || c->ks->nodalBc == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (m == 0) {
+    return 0;
+  }
+  NodalBcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs); p.idofs = conv(idofs); p.neighInt = conv(neigh_int);
+  if (!p.dofs.present() || !p.idofs.present() || !p.neighInt.present() || cell == nullptr || face == nullptr ||
+      kind == nullptr || tinv == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.cell = cell; p.face = face; p.kind = kind; p.tinv = tinv;
+  p.easiMap = easi_map; p.easiConst = easi_const; p.displacement = displacement; p.rhoG = rho_g;
+  p.m = m;
+  p.ldg = c->ldq;
+  return c->ks->nodalBc(p, static_cast<cudaStream_t>(stream));
 }
 
 int ssb_setup_cell_matrices(ssb_ctx* c, const double* coords, const long long* neighbors, const double* material,

@@ -8,6 +8,7 @@
 #ifdef SSB_HAVE_TC
 #include "kernels_tc.cuh"
 #endif
+#include "kernels_nodal.cuh"
 
 #define SSB_CAT2(a, b) a##b
 #define SSB_CAT(a, b) SSB_CAT2(a, b)
@@ -339,7 +340,25 @@ int accumulateEntry(const AccumulateParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
-const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry, accumulateEntry, taylorFpEntry};
+struct GenNodal {
+  static constexpr int kB2 = SSB_CAT(gen_nodal_o, SSB_ORDER)::kB2;
+  template <typename R>
+  __device__ __forceinline__ static const R* nodalV() { return SSB_CAT(gen_nodal_o, SSB_ORDER)::nodalV<R>(); }
+  template <typename R>
+  __device__ __forceinline__ static const R* nodalP() { return SSB_CAT(gen_nodal_o, SSB_ORDER)::nodalP<R>(); }
+};
+
+int nodalBcEntry(const NodalBcParams& p, cudaStream_t stream) {
+  if (p.m <= 0) {
+    return 0;
+  }
+  constexpr int W = 4;
+  k_local_nodal_bc<Real, Gen, GenNodal, W><<<unsigned((p.m + W - 1) / W), 32 * W, 0, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
+const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry, accumulateEntry, taylorFpEntry,
+                        nodalBcEntry};
 
 }  // namespace
 

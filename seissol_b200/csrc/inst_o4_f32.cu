@@ -4,6 +4,7 @@
 #define SSB_MINB_LOCAL 4
 #define SSB_MINB_NEIGH 4
 #include "gen/ops_o4.cuh"
+#include "gen/nodal_o4.cuh"
 #include "gen/tc_o4.cuh"
 #define SSB_HAVE_TC 1
 #define SSB_ORDER 4

@@ -1,5 +1,6 @@
 // Kernel instantiation: elastic, order 4, double.
 #include "gen/ops_o4.cuh"
+#include "gen/nodal_o4.cuh"
 #define SSB_ORDER 4
 #define SSB_REAL double
 #define SSB_TAG o4_f64

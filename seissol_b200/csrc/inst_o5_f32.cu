@@ -4,6 +4,7 @@
 #define SSB_MINB_LOCAL 3
 #define SSB_MINB_NEIGH 3
 #include "gen/ops_o5.cuh"
+#include "gen/nodal_o5.cuh"
 #include "gen/tc_o5.cuh"
 #define SSB_HAVE_TC 1
 #define SSB_ORDER 5

@@ -1,5 +1,6 @@
 // Kernel instantiation: elastic, order 5, double.
 #include "gen/ops_o5.cuh"
+#include "gen/nodal_o5.cuh"
 #define SSB_ORDER 5
 #define SSB_REAL double
 #define SSB_TAG o5_f64

@@ -6,6 +6,7 @@
 #define SSB_MINB_NEIGHFP 3
 #endif
 #include "gen/ops_o6.cuh"
+#include "gen/nodal_o6.cuh"
 #include "gen/tc_o6.cuh"
 #define SSB_HAVE_TC 1
 #define SSB_ORDER 6

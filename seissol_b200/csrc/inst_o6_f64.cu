@@ -1,5 +1,6 @@
 // Kernel instantiation: elastic, order 6, double.
 #include "gen/ops_o6.cuh"
+#include "gen/nodal_o6.cuh"
 #define SSB_ORDER 6
 #define SSB_REAL double
 #define SSB_TAG o6_f64

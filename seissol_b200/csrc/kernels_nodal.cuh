@@ -1,0 +1,167 @@
+// Nodal boundary conditions of the local integral: Dirichlet (easi boundary map) and FreeSurfaceGravity faces.
+//
+// Reference: Local::computeIntegral, src/Kernels/LinearCK/Local.cpp:157-252 (batched :350-455 through
+// DirichletBoundary::evaluateOnDevice, src/Kernels/LinearCK/DirichletBoundary.h:67-118), generated kernels
+// projectToNodalBoundaryRotated, createEasiBoundaryGhostCells (codegen/kernels/nodalbc.py:55-85) and localFluxNodal
+// (codegen/kernels/aderdg.py:336-352).  Per boundary face (cell c, local face f):
+//   N      = V3mTo2nFace_f . I_c                  time-integrated DOFs at the B2 face nodes        [B2 x 9]
+//   INodal = N . Tinv^T                           rotated into the face-aligned frame
+//   Dirichlet (FaceType 4):          INodal(l, a) = sum_b map(a, b, l) INodal(l, b) + const(a, l)
+//   FreeSurfaceGravity (FaceType 2): INodal(l, 0..2) = 2 p - INodal(l, 0..2),  p = -rho g displacement(l)
+//   Q_c   += project2nFaceTo3m_f . (INodal . AminusT_f)                                             [B x 9]
+// One warp per boundary face: lanes are the face nodes for the first three steps and the basis rows (lane, lane + 32)
+// for the last; the two dense operators come from lane-fastest tables (gen_nodal.py).  Boundary faces are a surface
+// set (few per cent of the cells), so this kernel is far from the roofline of the volume kernels by design.  Two
+// boundary faces of ONE cell may run concurrently: Q is updated with atomic adds.
+#pragma once
+#include "common.cuh"
+#include "params.cuh"
+
+namespace ssb {
+
+struct NodalBcParams {
+  ElemArray dofs, idofs, neighInt;
+  const long long* cell;      // [m]
+  const uint8_t* face;        // [m]
+  const uint8_t* kind;        // [m] FaceType: 4 = Dirichlet, 2 = FreeSurfaceGravity (others: face skipped)
+  const void* tinv;           // [m][9][9] row-major Tinv(p, q)
+  const void* easiMap;        // [m][9][9][B2] (a, b, l), Dirichlet faces
+  const void* easiConst;      // [m][9][B2]
+  const void* displacement;   // [m][B2], FreeSurfaceGravity faces
+  const void* rhoG;           // [m] rho * g
+  long long m;
+  int ldg;
+};
+
+template <typename R, typename G, typename GN, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcParams p) {
+  constexpr int B = G::kB, B2 = GN::kB2;
+  __shared__ R sI[WARPS][9 * B];        // I of the cell, [q][k]
+  __shared__ R sT[WARPS][81 + 3];       // Tinv, then AminusT
+  __shared__ R sZ[WARPS][32 * 9];       // node values [l][9]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long i = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  if (i >= p.m) {
+    return;
+  }
+  const int kind = p.kind[i];
+  if (kind != 4 && kind != 2) {
+    return;   // warp-uniform
+  }
+  const long long c = p.cell[i];
+  const int f = p.face[i];
+  const R* const Ic = static_cast<const R*>(p.idofs.at(c));
+  for (int q = 0; q < 9; ++q) {
+    for (int k = lane; k < B; k += 32) {
+      sI[warp][q * B + k] = Ic[q * p.ldg + k];
+    }
+  }
+  const R* const tinv = static_cast<const R*>(p.tinv) + 81 * i;
+  for (int e = lane; e < 81; e += 32) {
+    sT[warp][e] = tinv[e];
+  }
+  __syncwarp();
+  // ---- N(l, q) = sum_k V(l, k) I(k, q), lane = node l
+  R nq[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    nq[q] = R(0);
+  }
+  const R* V = GN::template nodalV<R>() + static_cast<size_t>(f) * B * 32 + lane;
+#pragma unroll 4
+  for (int k = 0; k < B; ++k) {
+    const R v = V[k * 32];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      nq[q] = fma(v, sI[warp][q * B + k], nq[q]);
+    }
+  }
+  // ---- INodal(l, p') = sum_q N(l, q) Tinv(p', q)
+  R in[9];
+#pragma unroll
+  for (int pp = 0; pp < 9; ++pp) {
+    R a = R(0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      a = fma(nq[q], sT[warp][9 * pp + q], a);
+    }
+    in[pp] = a;
+  }
+  // ---- the boundary condition at the node
+  if (lane < B2) {
+    if (kind == 4) {
+      const R* map = static_cast<const R*>(p.easiMap) + static_cast<size_t>(i) * 81 * B2 + lane;
+      const R* cst = static_cast<const R*>(p.easiConst) + static_cast<size_t>(i) * 9 * B2 + lane;
+      R out[9];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        R s = cst[a * B2];
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          s = fma(map[(a * 9 + b) * B2], in[b], s);
+        }
+        out[a] = s;
+      }
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        in[a] = out[a];
+      }
+    } else {
+      const R pressure = -static_cast<const R*>(p.rhoG)[i] * static_cast<const R*>(p.displacement)[i * B2 + lane];
+      in[0] = R(2) * pressure - in[0];
+      in[1] = R(2) * pressure - in[1];
+      in[2] = R(2) * pressure - in[2];
+    }
+  }
+  __syncwarp();   // everybody is done with Tinv
+  const R* const A = static_cast<const R*>(p.neighInt.at(c)) + 81 * f;
+  for (int e = lane; e < 81; e += 32) {
+    sT[warp][e] = A[e];   // AminusT, memory A[o + 9 p']
+  }
+  __syncwarp();
+  // ---- Z(l, p') = sum_o INodal(l, o) AminusT(o, p')
+#pragma unroll
+  for (int pp = 0; pp < 9; ++pp) {
+    R a = R(0);
+#pragma unroll
+    for (int o = 0; o < 9; ++o) {
+      a = fma(in[o], sT[warp][o + 9 * pp], a);
+    }
+    sZ[warp][lane * 9 + pp] = lane < B2 ? a : R(0);
+  }
+  __syncwarp();
+  // ---- Q(k, p') += sum_l P(k, l) Z(l, p'), lane = rows k = lane, lane + 32
+  R acc[2][9];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) {
+      acc[r][pp] = R(0);
+    }
+  }
+  const R* P = GN::template nodalP<R>() + static_cast<size_t>(f) * B2 * 64 + lane;
+#pragma unroll 3
+  for (int l = 0; l < B2; ++l) {
+    const R p0 = P[l * 64], p1 = P[l * 64 + 32];
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) {
+      const R zv = sZ[warp][l * 9 + pp];
+      acc[0][pp] = fma(p0, zv, acc[0][pp]);
+      acc[1][pp] = fma(p1, zv, acc[1][pp]);
+    }
+  }
+  R* const Q = static_cast<R*>(const_cast<void*>(p.dofs.at(c)));
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int k = lane + 32 * r;
+    if (k < B) {
+#pragma unroll
+      for (int pp = 0; pp < 9; ++pp) {
+        atomicAdd(Q + pp * p.ldg + k, acc[r][pp]);
+      }
+    }
+  }
+}
+
+}  // namespace ssb

@@ -339,3 +339,34 @@ def test_invalid_arguments_are_rejected(gpu):
     torch.cuda.synchronize()
     assert torch.equal(before, d.dofs)
     assert b"invalid" in lib.ssb_error_string(-1)
+
+
+@pytest.mark.parametrize("order,dt", [(4, np.float32), (6, np.float32), (6, np.float64)])
+def test_local_nodal_boundary_conditions(gpu, order, dt):
+    """ssb_local_nodal_bc (Dirichlet with an easi boundary map, FreeSurfaceGravity) against the oracle, whose nodal
+    path is pinned against the reference's generated kernels (tests/test_oracle_dr.py).  Some cells carry two boundary
+    faces (atomic adds)."""
+    from test_oracle_dr import nodal_bc_case
+    torch, api, proxy = gpu
+    n, m = 61, 90
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy)
+    rng = np.random.default_rng(33)
+    B2 = order * (order + 1) // 2
+    I = rng.uniform(-1, 1, host["Q"].shape).astype(dt)
+    bc = nodal_bc_case(rng, n, m, B2, dt)
+    bc["kind"][::9] = 0      # a face type without a nodal boundary condition: skipped
+    tab64 = O.load_tables(order, np.float64)
+    want = O.local_nodal_bc(tab64, host["Q"].astype(np.float64), I.astype(np.float64), O.flux_dense(host["Aminus"]).astype(np.float64),
+                            {k: (v.astype(np.float64) if v.dtype.kind == "f" else v) for k, v in bc.items()})
+    dev = data.dofs.device
+    data = proxy.ProxyData.from_host(ctx, dict(host, I=I))
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    ctx.local_nodal_bc(api.strided(data.dofs), api.strided(data.buffers), api.strided(data.neigh_int), d(bc["cell"]),
+                       d(bc["face"]), d(bc["kind"]), d(bc["tinv"]), d(bc["easiMap"]), d(bc["easiConst"]), d(bc["displacement"]),
+                       d(bc["rhoG"].astype(dt)), m)
+    torch.cuda.synchronize()
+    got = data.to_logical(data.dofs).astype(np.float64)
+    t = 5e-6 if dt == np.float32 else 1e-13
+    assert rel_l2(got, want) < t
+    assert rel_l2(got - host["Q"], want - host["Q"]) < 10 * t
+    assert np.unique(bc["cell"]).size < m      # at least one cell with two boundary faces

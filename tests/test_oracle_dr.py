@@ -13,6 +13,7 @@ import pytest
 
 from conftest import rel_l2
 from oracle import aderdg as O
+from oracle import ref_lib
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 sys.path.insert(0, GOLDEN)
@@ -67,3 +68,41 @@ def test_dr_oracle_matches_reference_library(cfg, order, dt):
     want = R.neighbor(c["Q"], x["I"], c["neighbors"], c["Aminus"], c["face_rel"], x["ft"], dr=x["dr"])
     assert rel_l2(got, want) < tol(dt)
     assert rel_l2(got - c["Q"], want - c["Q"]) < tol(dt)
+
+
+def nodal_bc_case(rng, n, m, B2, dt):
+    """m boundary faces on random (cell, face) slots: Dirichlet (easi map + constant) and FreeSurfaceGravity faces with
+    a random rotation Tinv."""
+    slots = rng.choice(4 * n, size=m, replace=False)
+    kind = np.where(rng.uniform(size=m) < 0.5, 4, 2).astype(np.uint8)
+    return {
+        "cell": (slots // 4).astype(np.int64), "face": (slots % 4).astype(np.uint8), "kind": kind,
+        "tinv": rng.uniform(-1, 1, (m, 9, 9)).astype(dt),
+        "easiMap": rng.uniform(-1, 1, (m, 9, 9, B2)).astype(dt),
+        "easiConst": rng.uniform(-1, 1, (m, 9, B2)).astype(dt),
+        "displacement": rng.uniform(-1, 1, (m, B2)).astype(dt),
+        "rhoG": rng.uniform(1.0, 3.0, m),
+    }
+
+
+@pytest.mark.parametrize("cfg,order,dt", [("elastic_o4_f32", 4, np.float32), ("elastic_o6_f32", 6, np.float32),
+                                          ("elastic_o6_f64", 6, np.float64)])
+def test_nodal_boundary_conditions_match_reference_library(cfg, order, dt):
+    """O.local_nodal_bc against the reference's generated projectToNodalBoundaryRotated, createEasiBoundaryGhostCells
+    and localFluxNodal kernels (Local.cpp:157-252)."""
+    if not ref_lib.available(cfg):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    R = ref_lib.RefLib(cfg)
+    tab = O.load_tables(order, dt)
+    rng = np.random.default_rng(21)
+    n, m = 17, 23
+    B2 = order * (order + 1) // 2
+    d = O.proxy_data(order, n, dt, seed=9)
+    I = rng.uniform(-1, 1, d["Q"].shape).astype(dt)
+    bc = nodal_bc_case(rng, n, m, B2, dt)
+    want = R.nodal_bc(d["Q"], I, d["Aminus"], bc)
+    got = O.local_nodal_bc(tab, d["Q"], I, O.flux_dense(d["Aminus"]), bc)
+    tol = 100 * np.finfo(dt).eps
+    assert rel_l2(got, want) < tol
+    assert rel_l2(got - d["Q"], want - d["Q"]) < 10 * tol
+    assert np.linalg.norm(got - d["Q"]) > 1e-3 * np.linalg.norm(d["Q"])

@@ -69,6 +69,7 @@ def build(ref, order):
     db = read_xml(os.path.join(mdir, f"matrices_{B}.xml"))
     dr = read_json(os.path.join(mdir, f"dr_stroud_matrices_{order}.json"))
     mass = read_json(os.path.join(mdir, f"mass_{order}.json"))
+    nodal = read_json(os.path.join(mdir, "nodal", f"nodalBoundary_matrices_{order}.json"))
     t = {
         "order": np.int64(order),
         "kDivM": family(db, "kDivM", 3),
@@ -89,6 +90,11 @@ def build(ref, order):
         "V3mTo2nTWDivM": np.stack(
             [dr[f"V3mTo2nTWDivM({s},{r})"] for r in range(4) for s in range(4)]
         ),
+        # nodal boundary conditions (codegen/kernels/nodalbc.py, aderdg.py:123-131): modal volume -> face nodes, face
+        # nodes -> modal face; project2nFaceTo3m(i) = rDivM(i) . V2nTo2m is formed by the consumers
+        "V3mTo2nFace": family(nodal, "V3mTo2nFace", 4),
+        "V2nTo2m": nodal["V2nTo2m"],
+        "nodes2D": nodal["nodes2D"],
     }
     return t
 
