@@ -13,7 +13,7 @@ Configurations (BASELINE.json `configs`):
   elastic_f64                   configs[1] in double precision
   o4                            configs[0]: ORDER=4 single precision, 100k elements
   visco                         configs[2]: viscoelastic2 (3 mechanisms) ORDER=5, 1M elements, `all`
-  dr_lsw | dr_rsfvw             configs[3]: 200k fault faces (50k cells): all_dr = local + godunov_dr + friction law + neigh_dr
+  dr_lsw | dr_rsfvw(_fast)      configs[3]: 200k fault faces (50k cells): all_dr = local + godunov_dr + friction law + neigh_dr
   lts (default, N > 1)          configs[4]: ONE cube mesh partitioned across the GPUs (x slabs, ~2.5M tetrahedra per GPU =
                                 ~20M at N = 8), clustered LTS rate 2 (3 clusters), per-cluster NVLink halo exchange;
                                 prints `parity_rel_l2` of a small partitioned run against the single-GPU run
@@ -43,6 +43,9 @@ CONFIGS = {
     "dr_lsw": dict(kind="dr", law="lsw", order=6, real=4, cells=50_000, ref="elastic_o6_f32", baseline="configs[3], linear slip weakening"),
     "dr_rsfvw": dict(kind="dr", law="rsfvw", order=6, real=4, cells=50_000, ref="elastic_o6_f32",
                      baseline="configs[3], rate-and-state fast velocity weakening"),
+    # the same with ssb_friction_params_t::rs_float_resolution_exit = 1 (Newton iterations stop at float resolution)
+    "dr_rsfvw_fast": dict(kind="dr", law="rsfvw", order=6, real=4, cells=50_000, ref="elastic_o6_f32", float_exit=True,
+                          baseline="configs[3], rate-and-state fast velocity weakening, float-resolution Newton exit"),
 }
 LTS_CELLS_PER_GPU = 2_500_000
 # vector-FMA peak MEASURED on this pool (tools/ubench/fma_peak.cu -> profiles/r2_ubench_fma_peak.txt): FFMA 73.4 TFLOP/s
@@ -241,7 +244,8 @@ class DrWorkload(Workload):
         self.dr, self.fric = shared
         self.faces = self.dr.faces
         self.k = proxy.DrProxyKernels(self.ctx, data, self.dr)
-        self.fparams, _, _ = proxy.friction_params(self.order, 1e-3, full_update_time=0.0)
+        self.fparams, _, _ = proxy.friction_params(self.order, 1e-3, full_update_time=0.0,
+                                                       rs_float_resolution_exit=bool(cfg.get("float_exit", False)))
         self.torch = torch
         self.name = (f"proxy all_dr + friction ({'linear slip weakening' if self.law == 'lsw' else 'rate-and-state fast velocity weakening'}), "
                      f"elastic ORDER={self.order} {'single' if self.real == 4 else 'double'} precision, {self.faces} fault faces = "

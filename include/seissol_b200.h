@@ -210,6 +210,14 @@ typedef struct ssb_friction_params {
   int energies_from_across_fault_velocities;  /* drParameters.energiesFromAcrossFaultVelocities (friction energy output) */
   double nucleation_t0[4]; /* drParameters.t0[i]: effective rise time of nucleation i (t0[0] is also `t0` above) */
   double nucleation_s0[4]; /* drParameters.s0[i]: onset time of nucleation i */
+  /* Rate-and-state in SINGLE precision: the reference's absolute Newton tolerances (1e-8) lie below the float
+   * resolution of slip rates of O(1): its float build never converges and always runs all 10 x 60 iterations.
+   * 0 (default): the same behaviour, iteration for iteration.  1: an iteration also counts as converged when the
+   * residual is at the rounding level of its operands (|g| <= 8 eps max(|a|, V)), i.e. when further iterations only
+   * move the iterate among neighbouring floats; results agree with mode 0 to a few ulp of the slip rate and the step
+   * is ~10 x faster.  No effect in double precision (8 eps |V| << 1e-8). */
+  int rs_float_resolution_exit;
+  int reserved;
 } ssb_friction_params_t;
 
 /* FrictionSolver::evaluate (src/DynamicRupture/FrictionLaws/FrictionSolver.h:41) for

@@ -52,7 +52,8 @@ class SsbFrictionParams(ctypes.Structure):
                 ("rs_slip_rate_tolerance", ctypes.c_double), ("rs_state_tolerance", ctypes.c_double),
                 ("rs_max_number_slip_rate_updates", ctypes.c_int), ("rs_number_state_variable_updates", ctypes.c_int),
                 ("nucleation_count", ctypes.c_int), ("energies_from_across_fault_velocities", ctypes.c_int),
-                ("nucleation_t0", ctypes.c_double * 4), ("nucleation_s0", ctypes.c_double * 4)]
+                ("nucleation_t0", ctypes.c_double * 4), ("nucleation_s0", ctypes.c_double * 4),
+                ("rs_float_resolution_exit", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class SsbError(RuntimeError):

@@ -647,6 +647,7 @@ int friction(ssb_ctx* c, const ssb_friction_data_t* d, const ssb_friction_params
   p.rsSr0 = q->rs_sr0;
   p.rsSlipRateTolerance = q->rs_slip_rate_tolerance;
   p.rsStateTolerance = q->rs_state_tolerance;
+  p.rsFloatResolutionExit = (c->realSize == 4 && q->rs_float_resolution_exit != 0) ? 1 : 0;
   p.rsMaxNumberSlipRateUpdates = q->rs_max_number_slip_rate_updates;
   p.rsNumberStateVariableUpdates = q->rs_number_state_variable_updates;
   return c->dr->friction(p, law, static_cast<cudaStream_t>(stream));

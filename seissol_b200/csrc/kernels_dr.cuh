@@ -436,7 +436,12 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
         for (int i = 0; i < p.rsMaxNumberSlipRateUpdates; ++i) {
           const R muF = rsA * rsArsinhexp<R>(cLin * test, cExpLog, cExp);
           g = -invEtaS * (fabs(normal) * muF - shear) - test;
-          const bool ok = !active || fabs(g) < static_cast<R>(p.rsSlipRateTolerance);
+          // (rsFloatResolutionExit, single precision only: the residual g = a - V cannot be resolved below the rounding
+          //  level of a and V; the reference's float build keeps iterating among neighbouring floats until the cap)
+          const R aTerm = g + test;
+          const bool atResolution = p.rsFloatResolutionExit != 0 &&
+                                    fabs(g) <= R(8) * R(1.1920929e-7) * fmax(fabs(aTerm), test);
+          const bool ok = !active || fabs(g) < static_cast<R>(p.rsSlipRateTolerance) || atResolution;
           if (__syncthreads_and(ok)) {
             mu = muF;
             faceConverged = true;
@@ -447,10 +452,13 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
           test = max(rsAlmostZero<R>(), test - g / dG);
         }
         if (!faceConverged) {
-          convInner = convInner && fabs(g) < static_cast<R>(p.rsSlipRateTolerance);
+          convInner = convInner && (fabs(g) < static_cast<R>(p.rsSlipRateTolerance) ||
+                                    (p.rsFloatResolutionExit != 0 &&
+                                     fabs(g) <= R(8) * R(1.1920929e-7) * fmax(fabs(g + test), test)));
         }
         localSr = R(0.5) * (srm + test);
-        outerPre = fabs(test - srm) < static_cast<R>(p.rsStateTolerance);
+        outerPre = fabs(test - srm) < static_cast<R>(p.rsStateTolerance) ||
+                   (p.rsFloatResolutionExit != 0 && fabs(test - srm) <= R(8) * R(1.1920929e-7) * fmax(test, srm));
         srm = test;
         if (__syncthreads_and(!active || outerPre)) {
           break;

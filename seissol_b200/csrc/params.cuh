@@ -124,6 +124,7 @@ struct FrictionParams {
   const void* spaceWeights;         // [P]
   const void* doubledSurfaceArea;   // [n]
   int energiesFromAcrossFaultVelocities;
+  int rsFloatResolutionExit;        // single precision: accept a Newton iterate at the rounding level of its operands
 };
 
 struct NeighDrParams {

@@ -307,6 +307,7 @@ def friction_params(order, dt, full_update_time=0.0, **kw):
     p.rs_number_state_variable_updates = kw.get("rs_number_state_variable_updates", 10)
     nuc_t0, nuc_s0 = kw.get("nucleation_t0", []), kw.get("nucleation_s0", [])
     p.energies_from_across_fault_velocities = 1 if kw.get("energies_from_across_fault_velocities", False) else 0
+    p.rs_float_resolution_exit = 1 if kw.get("rs_float_resolution_exit", False) else 0
     p.nucleation_count = len(nuc_t0)
     for i in range(len(nuc_t0)):
         p.nucleation_t0[i], p.nucleation_s0[i] = float(nuc_t0[i]), float(nuc_s0[i])

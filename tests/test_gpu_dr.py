@@ -403,7 +403,7 @@ def _round_inputs(pb, dt):
 
 @pytest.mark.parametrize("law,order,dt,n,m", [("lsw", 6, np.float32, 8000, 10400), ("lsw", 6, np.float64, 1500, 2000),
                                                ("rsfvw", 6, np.float64, 300, 320), ("rsfvw", 6, np.float32, 300, 320),
-                                               ("lsw", 4, np.float32, 1500, 2000)])
+                                               ("rsfvw-fast", 6, np.float32, 300, 320), ("lsw", 4, np.float32, 1500, 2000)])
 def test_all_dr_friction_n_steps(gpu, law, order, dt, n, m):
     """BASELINE.json's bar on the fault path: 10 time steps of the full chain on the device -- ader (+ derivatives) ->
     local (fault faces skipped) -> godunov_dr -> friction law (state carried from step to step) -> neigh (regular faces)
@@ -411,6 +411,10 @@ def test_all_dr_friction_n_steps(gpu, law, order, dt, n, m):
     inputs rounded to the device precision: Q within 1e-5 (single) / 1e-11 (double); imposed state and the friction
     state within the bounds documented below.  The first case has > 10 000 fault faces."""
     torch, api, proxy = gpu
+    # "rsfvw-fast": ssb_friction_params_t::rs_float_resolution_exit = 1 (the Newton iterations stop at float resolution
+    # instead of running into the iteration caps like the reference's float build): same bounds as the reference mode
+    fast = law.endswith("-fast")
+    law = law.split("-")[0]
     steps, step = 10, 1e-3
     es = np.dtype(dt).itemsize
     ctx = api.Context(order, es)
@@ -457,7 +461,8 @@ def test_all_dr_friction_n_steps(gpu, law, order, dt, n, m):
     for s in range(steps):
         t_now = s * step
         fp, dts, wts = proxy.friction_params(order, step, full_update_time=t_now, rs_sr0=pb["params"].rsSr0,
-                                             healing_threshold=pb["params"].healingThreshold, t0=pb["params"].t0)
+                                             healing_threshold=pb["params"].healingThreshold, t0=pb["params"].t0,
+                                             rs_float_resolution_exit=fast)
         # ---- oracle chain (double precision)
         I, ders = O.ader(tab, Q, star, c_int, True)
         q_loc = O.local(tab, Q, I, star, O.flux_dense(host["Aplus"]), ft)
