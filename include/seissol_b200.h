@@ -213,9 +213,9 @@ typedef struct ssb_friction_params {
   /* Rate-and-state in SINGLE precision: the reference's absolute Newton tolerances (1e-8) lie below the float
    * resolution of slip rates of O(1): its float build never converges and always runs all 10 x 60 iterations.
    * 0 (default): the same behaviour, iteration for iteration.  1: an iteration also counts as converged when the
-   * residual is at the rounding level of its operands (|g| <= 8 eps max(|a|, V)), i.e. when further iterations only
-   * move the iterate among neighbouring floats; results agree with mode 0 to a few ulp of the slip rate and the step
-   * is ~10 x faster.  No effect in double precision (8 eps |V| << 1e-8). */
+   * residual g = (shear - |normal| mu) / eta - V is at the rounding level of its terms,
+   * |g| <= 8 eps ((shear + |normal| mu) / eta + V), i.e. when further iterations only move the iterate among
+   * neighbouring floats.  Ignored in double precision. */
   int rs_float_resolution_exit;
   int reserved;
 } ssb_friction_params_t;

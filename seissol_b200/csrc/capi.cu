@@ -226,6 +226,11 @@ int ssb_create(ssb_ctx** out, int order, int real_size, int equation, int mechan
   c->ksAder = ks;
   c->ksLocal = (real_size == 8 && ks4 != nullptr) ? ks4 : ks;
   c->ksNeigh = c->ksLocal;
+  if (const char* e = std::getenv("SSB_ADER_GEN")) {  // A/B measurements: predictor on generation 4
+    if (e[0] == '4' && ks4 != nullptr) {
+      c->ksAder = ks4;
+    }
+  }
   if (forced == 3 || (forced == 4 && ks4 != nullptr)) {
     c->ks = c->ksAder = c->ksLocal = c->ksNeigh = forced == 4 ? ks4 : ks;
   }

@@ -121,7 +121,14 @@ template <> struct Pk<float> { using T = float2; static constexpr int V = 2; };
 #else
 template <> struct Pk<float> { using T = float; static constexpr int V = 1; };
 #endif
+#ifndef SSB_PACK_F64
+#define SSB_PACK_F64 1  // 2: two elements per thread in double precision (one materialised constant feeds two DFMAs)
+#endif
+#if SSB_PACK_F64 == 2
+template <> struct Pk<double> { using T = double2; static constexpr int V = 2; };
+#else
 template <> struct Pk<double> { using T = double; static constexpr int V = 1; };
+#endif
 
 __device__ __forceinline__ unsigned long long pk_bits(float2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
 __device__ __forceinline__ float2 pk_unbits(unsigned long long a) { return *reinterpret_cast<float2*>(&a); }
@@ -158,18 +165,36 @@ __device__ __forceinline__ double pk_mul(double a, double b) { return a * b; }
 __device__ __forceinline__ double pk_add(double a, double b) { return a + b; }
 __device__ __forceinline__ double pk_fmac(double c, double x, double acc) { return fma(c, x, acc); }
 __device__ __forceinline__ double pk_mulc(double c, double x) { return c * x; }
+// packed double: two elements per thread.  DFMA has no immediate operand: a literal costs two 32-bit moves, which two
+// elements now share (tools/ubench/gen_cbank2.py: 0.11 -> 0.34 DFMA/clk/SMSP at 8 warps per SM)
+__device__ __forceinline__ double2 pk_fma(double2 a, double2 b, double2 c) {
+  return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y));
+}
+__device__ __forceinline__ double2 pk_mul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 pk_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 pk_fmac(double c, double2 x, double2 acc) {
+  return make_double2(fma(c, x.x, acc.x), fma(c, x.y, acc.y));
+}
+__device__ __forceinline__ double2 pk_mulc(double c, double2 x) { return make_double2(c * x.x, c * x.y); }
 template <typename R> __device__ __forceinline__ typename Pk<R>::T pk_zero();
 #if SSB_PACK_F32 == 2
 template <> __device__ __forceinline__ float2 pk_zero<float>() { return make_float2(0.f, 0.f); }
 #else
 template <> __device__ __forceinline__ float pk_zero<float>() { return 0.f; }
 #endif
+#if SSB_PACK_F64 == 2
+template <> __device__ __forceinline__ double2 pk_zero<double>() { return make_double2(0.0, 0.0); }
+#else
 template <> __device__ __forceinline__ double pk_zero<double>() { return 0.0; }
+#endif
 // lane v of a packed value / packed value from per-lane scalars
 __device__ __forceinline__ float pk_get(float2 a, int v) { return v == 0 ? a.x : a.y; }
 __device__ __forceinline__ double pk_get(double a, int) { return a; }
 __device__ __forceinline__ float2 pk_make(const float (&a)[2]) { return make_float2(a[0], a[1]); }
 __device__ __forceinline__ double pk_make(const double (&a)[1]) { return a[0]; }
+__device__ __forceinline__ double pk_get(double2 a, int v) { return v == 0 ? a.x : a.y; }
+__device__ __forceinline__ double2 pk_make(const double (&a)[2]) { return make_double2(a[0], a[1]); }
+__device__ __forceinline__ double2 pk_sel01(double2 a, double2 b) { return make_double2(a.x, b.y); }
 // keep lane 0 of a, lane 1 of b
 __device__ __forceinline__ float2 pk_sel01(float2 a, float2 b) { return make_float2(a.x, b.y); }
 __device__ __forceinline__ double pk_sel01(double a, double) { return a; }
@@ -181,6 +206,9 @@ __device__ __forceinline__ float2 pk_keep(float2 a, const bool (&keep)[2]) {
 }
 __device__ __forceinline__ float pk_keep(float a, const bool (&keep)[1]) { return keep[0] ? a : 0.f; }
 __device__ __forceinline__ double pk_keep(double a, const bool (&keep)[1]) { return keep[0] ? a : 0.0; }
+__device__ __forceinline__ double2 pk_keep(double2 a, const bool (&keep)[2]) {
+  return make_double2(keep[0] ? a.x : 0.0, keep[1] ? a.y : 0.0);
+}
 
 // 4 consecutive packed entries from a lane-interleaved column ([k][V] reals)
 __device__ __forceinline__ void ldv4(float2 (&v)[4], const float* p) {
@@ -190,11 +218,19 @@ __device__ __forceinline__ void ldv4(float2 (&v)[4], const float* p) {
   v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
 }
 __device__ __forceinline__ void ldv4(double (&v)[4], const double* p) { ld4(v, p); }
+__device__ __forceinline__ void ldv4(double2 (&v)[4], const double* p) {
+  v[0] = *reinterpret_cast<const double2*>(p); v[1] = *reinterpret_cast<const double2*>(p + 2);
+  v[2] = *reinterpret_cast<const double2*>(p + 4); v[3] = *reinterpret_cast<const double2*>(p + 6);
+}
 __device__ __forceinline__ void stv4(float* p, float2 a, float2 b, float2 c, float2 d) {
   *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
   *reinterpret_cast<float4*>(p + 4) = make_float4(c.x, c.y, d.x, d.y);
 }
 __device__ __forceinline__ void stv4(double* p, double a, double b, double c, double d) { st4(p, a, b, c, d); }
+__device__ __forceinline__ void stv4(double* p, double2 a, double2 b, double2 c, double2 d) {
+  *reinterpret_cast<double2*>(p) = a; *reinterpret_cast<double2*>(p + 2) = b;
+  *reinterpret_cast<double2*>(p + 4) = c; *reinterpret_cast<double2*>(p + 6) = d;
+}
 
 // 2 consecutive packed entries (one 128-bit access for float2 / double, 64-bit for scalar float)
 __device__ __forceinline__ void ldv2(float2 (&v)[2], const float* p) {
@@ -209,6 +245,12 @@ __device__ __forceinline__ void ldv2(double (&v)[2], const double* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
   v[0] = a.x; v[1] = a.y;
 }
+__device__ __forceinline__ void ldv2(double2 (&v)[2], const double* p) {
+  v[0] = *reinterpret_cast<const double2*>(p); v[1] = *reinterpret_cast<const double2*>(p + 2);
+}
+__device__ __forceinline__ void stv2(double* p, double2 a, double2 b) {
+  *reinterpret_cast<double2*>(p) = a; *reinterpret_cast<double2*>(p + 2) = b;
+}
 __device__ __forceinline__ void stv2(float* p, float2 a, float2 b) {
   *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
 }
@@ -221,6 +263,9 @@ __device__ __forceinline__ void st2lane(float* p, int v, float2 a, float2 b) {
 __device__ __forceinline__ void st2lane(float* p, int, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st2lane(double* p, int, double a, double b) {
   *reinterpret_cast<double2*>(p) = make_double2(a, b);
+}
+__device__ __forceinline__ void st2lane(double* p, int v, double2 a, double2 b) {
+  *reinterpret_cast<double2*>(p) = v == 0 ? make_double2(a.x, b.x) : make_double2(a.y, b.y);
 }
 
 // Operand sources of the generated sparse mat-vec code: a lane-interleaved column, or V
@@ -251,12 +296,26 @@ template <> struct SrcSplit<double> {
   const double* p0; const double* p1;
   __device__ __forceinline__ void load4(double (&v)[4], int k0) const { ld4(v, p0 + k0); }
   __device__ __forceinline__ void load2(double (&v)[2], int k0) const { ldv2(v, p0 + k0); }
+  __device__ __forceinline__ void load4(double2 (&v)[4], int k0) const {
+    double a[4], b[4];
+    ld4(a, p0 + k0); ld4(b, p1 + k0);
+    v[0] = make_double2(a[0], b[0]); v[1] = make_double2(a[1], b[1]);
+    v[2] = make_double2(a[2], b[2]); v[3] = make_double2(a[3], b[3]);
+  }
+  __device__ __forceinline__ void load2(double2 (&v)[2], int k0) const {
+    const double2 a = *reinterpret_cast<const double2*>(p0 + k0);
+    const double2 b = *reinterpret_cast<const double2*>(p1 + k0);
+    v[0] = make_double2(a.x, b.x); v[1] = make_double2(a.y, b.y);
+  }
 };
 // lane v of 4 packed values -> one 128-bit (float) / 256-bit (double) store
 __device__ __forceinline__ void st4lane(float* p, int v, float2 a, float2 b, float2 c, float2 d) {
   st4(p, pk_get(a, v), pk_get(b, v), pk_get(c, v), pk_get(d, v));
 }
 __device__ __forceinline__ void st4lane(double* p, int, double a, double b, double c, double d) { st4(p, a, b, c, d); }
+__device__ __forceinline__ void st4lane(double* p, int v, double2 a, double2 b, double2 c, double2 d) {
+  st4(p, pk_get(a, v), pk_get(b, v), pk_get(c, v), pk_get(d, v));
+}
 
 
 // scalar type of a packed lane type, zero of a packed lane type, scalar broadcast
@@ -264,14 +323,17 @@ template <typename PT> struct PkScalar;
 template <> struct PkScalar<float2> { using T = float; static constexpr int V = 2; };
 template <> struct PkScalar<float> { using T = float; static constexpr int V = 1; };
 template <> struct PkScalar<double> { using T = double; static constexpr int V = 1; };
+template <> struct PkScalar<double2> { using T = double; static constexpr int V = 2; };
 template <typename PT> __device__ __forceinline__ PT pk_zero_of();
 template <> __device__ __forceinline__ float2 pk_zero_of<float2>() { return make_float2(0.f, 0.f); }
 template <> __device__ __forceinline__ float pk_zero_of<float>() { return 0.f; }
 template <> __device__ __forceinline__ double pk_zero_of<double>() { return 0.0; }
+template <> __device__ __forceinline__ double2 pk_zero_of<double2>() { return make_double2(0.0, 0.0); }
 template <typename PT> __device__ __forceinline__ PT pk_bcast(typename PkScalar<PT>::T x);
 template <> __device__ __forceinline__ float2 pk_bcast<float2>(float x) { return make_float2(x, x); }
 template <> __device__ __forceinline__ float pk_bcast<float>(float x) { return x; }
 template <> __device__ __forceinline__ double pk_bcast<double>(double x) { return x; }
+template <> __device__ __forceinline__ double2 pk_bcast<double2>(double x) { return make_double2(x, x); }
 // Dynamic-rupture kernels always pack two TIME POINTS per thread in single precision.
 template <typename R> struct PkDr;
 template <> struct PkDr<float> { using T = float2; static constexpr int V = 2; };

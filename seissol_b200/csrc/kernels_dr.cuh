@@ -432,15 +432,16 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
         const R cExp = cExpLog > R(0) ? exp(-cExpLog) : exp(cExpLog);
         R test = srm;
         R g = R(0);
+        R resolution = R(0);
         bool faceConverged = false;
         for (int i = 0; i < p.rsMaxNumberSlipRateUpdates; ++i) {
           const R muF = rsA * rsArsinhexp<R>(cLin * test, cExpLog, cExp);
           g = -invEtaS * (fabs(normal) * muF - shear) - test;
-          // (rsFloatResolutionExit, single precision only: the residual g = a - V cannot be resolved below the rounding
-          //  level of a and V; the reference's float build keeps iterating among neighbouring floats until the cap)
-          const R aTerm = g + test;
-          const bool atResolution = p.rsFloatResolutionExit != 0 &&
-                                    fabs(g) <= R(8) * R(1.1920929e-7) * fmax(fabs(aTerm), test);
+          // (rsFloatResolutionExit, single precision only: g = invEtaS (shear - |normal| mu) - V is a difference of
+          //  stresses; it cannot be resolved below the rounding level of its terms, and |dG| >= 1 carries that level over
+          //  to V.  The reference's float build keeps iterating among neighbouring floats until the cap.)
+          resolution = R(8) * R(1.1920929e-7) * (invEtaS * (fabs(normal) * muF + shear) + test);
+          const bool atResolution = p.rsFloatResolutionExit != 0 && fabs(g) <= resolution;
           const bool ok = !active || fabs(g) < static_cast<R>(p.rsSlipRateTolerance) || atResolution;
           if (__syncthreads_and(ok)) {
             mu = muF;
@@ -453,12 +454,11 @@ __global__ void __launch_bounds__((P + 31) / 32 * 32) k_friction(const FrictionP
         }
         if (!faceConverged) {
           convInner = convInner && (fabs(g) < static_cast<R>(p.rsSlipRateTolerance) ||
-                                    (p.rsFloatResolutionExit != 0 &&
-                                     fabs(g) <= R(8) * R(1.1920929e-7) * fmax(fabs(g + test), test)));
+                                    (p.rsFloatResolutionExit != 0 && fabs(g) <= resolution));
         }
         localSr = R(0.5) * (srm + test);
         outerPre = fabs(test - srm) < static_cast<R>(p.rsStateTolerance) ||
-                   (p.rsFloatResolutionExit != 0 && fabs(test - srm) <= R(8) * R(1.1920929e-7) * fmax(test, srm));
+                   (p.rsFloatResolutionExit != 0 && fabs(test - srm) <= R(2) * resolution);
         srm = test;
         if (__syncthreads_and(!active || outerPre)) {
           break;

@@ -29,6 +29,7 @@ __host__ __device__ constexpr int halfThreads(int NP) { return (kNQ * NP + 31) /
 __device__ __forceinline__ void stLane1(float* p, float2 a, float2 b) { p[1] = a.y; p[3] = b.y; }
 __device__ __forceinline__ void stLane1(float*, float, float) {}
 __device__ __forceinline__ void stLane1(double*, double, double) {}
+__device__ __forceinline__ void stLane1(double* p, double2 a, double2 b) { p[1] = a.y; p[3] = b.y; }
 
 template <typename R, typename G, int NP>
 struct AderCtx4 {
@@ -312,6 +313,22 @@ __device__ __forceinline__ void localBody4(const LocalParams& p, unsigned char* 
               stv2(Fe + (q * B2P + 4 * pc + 2 * H) * V, F[2 * pc], F[2 * pc + 1]);
             }
           }
+        if constexpr (V > 1) {
+          // face projections for the neighbor kernel (kernels_faceproj.cuh): the packed rows leave the registers
+          // element by element (the shared-memory copy is lane-interleaved, no bulk store possible)
+          if (wantProj && active) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              if (el[v] >= 0) {
+                R* const dst = static_cast<R*>(const_cast<void*>(p.faceProj.at(el[v]))) + (f * kNQ + q) * B2P;
+#pragma unroll
+                for (int pc = 0; pc < B2P / 4; ++pc) {
+                  st2lane(dst + 4 * pc + 2 * H, v, F[2 * pc], F[2 * pc + 1]);
+                }
+              }
+            }
+          }
+        }
         }
         if constexpr (V == 1) {
           // face projections for the neighbor kernel (kernels_faceproj.cuh), see k_local

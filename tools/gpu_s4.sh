@@ -1,0 +1,21 @@
+#!/bin/bash
+# round-2 session 4 GPU steps (development aid): tools/gpu_s4.sh <tag> <step>...
+tag=$1; shift
+out=gpurun_out/$tag; mkdir -p $out
+L=$PWD/seissol_b200/lib
+QB="python tools/quick_bench.py --real 8 --cells 500000 --kernels ader,localwoader,neigh,all"
+for s in "$@"; do
+case $s in
+pd2)
+  for v in pd2 pd2n3; do
+    SSB_LIB=$L/libseissol_b200_$v.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/pytest_$v.log 2>&1; echo "exit $?" >> $out/pytest_$v.log
+    SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_$v.txt 2>&1
+    SSB_ADER_GEN=4 SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_${v}_ader4.txt 2>&1
+  done
+  timeout 300 $QB > $out/qb_f64_base.txt 2>&1 ;;
+rsfast)
+  timeout 600 python -m pytest tests/test_gpu_dr.py -m gpu -x -q -k "n_steps" > $out/pytest_dr.log 2>&1; echo "exit $?" >> $out/pytest_dr.log
+  timeout 300 python bench.py --config dr_rsfvw_fast --steps 5 --no-cpu > $out/bench_dr_rsfvw_fast.json 2> $out/bench_dr_rsfvw_fast.err ;;
+esac
+done
+for f in $out/*.log $out/*.txt $out/*.json; do echo "=== $f"; tail -c 1200 $f; done
