@@ -276,10 +276,19 @@ int ssb_visco_neigh_dr(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t dofs_ane, ssb
  * arrays in the precision of the context: tinv [m][9][9] row-major Tinv(p, q); easi_map [m][9][9][B2] (a, b, l) and
  * easi_const [m][9][B2] (Dirichlet faces; B2 = O(O+1)/2 face nodes); displacement [m][B2] and rho_g [m]
  * (FreeSurfaceGravity faces).  Faces of any other kind are skipped.  Two boundary faces of one cell are added with
- * atomic adds (their order is not fixed).  FaceType::Analytical (a user callback per node and time) is not covered. */
+ * atomic adds (their order is not fixed).  FaceType::Analytical faces: ssb_local_nodal_flux below. */
 int ssb_local_nodal_bc(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_array_t neigh_int, const long long* cell,
                        const uint8_t* face, const uint8_t* kind, const void* tinv, const void* easi_map,
                        const void* easi_const, const void* displacement, const void* rho_g, long long m, void* stream);
+
+/* FaceType::Analytical faces of the local integral (Local::evaluateBatchedTimeDependentBc, Local.cpp:397-455): the
+ * reference evaluates the analytical solution at the face nodes on the HOST (a user callback per node and time point,
+ * integrated over the time step by DirichletBoundary::evaluateTimeDependent, DirichletBoundary.h:121-165), stores the
+ * result in LTS::AnalyticScratch and launches the generated localFluxNodal on the device.  This entry point is that launch
+ * for m faces (cell[i], face[i]):   Q += project2nFaceTo3m_f . INodal_i . AminusT_f.
+ * inodal: DEVICE array [m][9][B2] (quantity a, node l; B2 = O(O+1)/2) in the precision of the context. */
+int ssb_local_nodal_flux(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t neigh_int, const long long* cell,
+                         const uint8_t* face, const void* inodal, long long m, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Set-up on the device (elastic): the per-element and per-fault-face matrices the entry points above consume, from

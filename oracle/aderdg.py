@@ -228,6 +228,24 @@ def local_nodal_bc(tab, Q, I, Aminus, bc):
     return out
 
 
+def analytical_inodal(evaluate, nodes, start_time, time_step_width, order):
+    """DirichletBoundary::evaluateTimeDependent (src/Kernels/LinearCK/DirichletBoundary.h:121-165) with
+    ApplyAnalyticalSolution (Local.cpp:86-118): INodal_i = sum_j w_j evaluate(nodes_i, t_j), Gauss-Legendre points of
+    [t, t + dt].  evaluate(nodes [B2, 3], t) -> [B2, 9]; returns [m, B2, 9]."""
+    t, w = gauss_legendre_shifted(order, start_time, start_time + time_step_width)
+    return np.stack([sum(wj * np.asarray(evaluate(nd, tj), dtype=np.float64) for tj, wj in zip(t, w)) for nd in nodes])
+
+
+def local_nodal_flux(tab, Q, Aminus, cell, face, inodal):
+    """FaceType::Analytical faces (Local.cpp:233-246, batched :409-452): localFluxNodal on GIVEN nodal values,
+    Q += (rDivM_f . V2nTo2m) . INodal . AminusT_f (codegen/kernels/aderdg.py:336-352).  inodal [m, B2, 9]."""
+    out = Q.copy()
+    for i in range(len(cell)):
+        c, f = int(cell[i]), int(face[i])
+        out[c] += (tab["rDivM"][f] @ tab["V2nTo2m"]) @ inodal[i] @ Aminus[c, f]
+    return out
+
+
 def dr_interpolate(tab, ders_plus, ders_minus, tinvT, face_info, coeffs):
     """DynamicRupture::spaceTimeInterpolation (src/Kernels/DynamicRupture.cpp:57-108):
     for each time point s: Q±(t_s) = sum_d coeffs[s,d] dQ±(d);

@@ -19,7 +19,7 @@ SYMBOLS = [
     "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj", "ssb_taylor_faceproj", "ssb_accumulate_rows",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh", "ssb_visco_neigh_dr",
-    "ssb_setup_cell_matrices", "ssb_setup_dr_matrices", "ssb_local_nodal_bc",
+    "ssb_setup_cell_matrices", "ssb_setup_dr_matrices", "ssb_local_nodal_bc", "ssb_local_nodal_flux",
     "ssb_error_string", "ssb_version",
 ]
 
@@ -101,6 +101,7 @@ def load_library():
     lib.ssb_visco_neigh.argtypes = [P, A, A, P, P, A, A, P, P, LL, P, P]
     lib.ssb_visco_neigh_dr.argtypes = [P, A, A, A, P, P, P, P, LL, P]
     lib.ssb_local_nodal_bc.argtypes = [P, A, A, A, P, P, P, P, P, P, P, P, LL, P]
+    lib.ssb_local_nodal_flux.argtypes = [P, A, A, P, P, P, LL, P]
     lib.ssb_setup_cell_matrices.argtypes = [P, P, P, P, P, A, A, LL, P]
     lib.ssb_setup_dr_matrices.argtypes = [P, P, P, P, P, P, P, P, P, P, P, LL, P]
     _lib = lib
@@ -262,6 +263,11 @@ class Context:
         _check(self.lib.ssb_local_nodal_bc(self.handle, dofs, idofs, neigh_int, _ptr(cell), _ptr(face), _ptr(kind), _ptr(tinv),
                                            _ptr(easi_map), _ptr(easi_const), _ptr(displacement), _ptr(rho_g), m,
                                            _stream(stream)))
+
+    def local_nodal_flux(self, dofs, neigh_int, cell, face, inodal, m, stream=None):
+        """FaceType::Analytical faces: nodal flux of GIVEN boundary values inodal [m, 9, B2] (see boundary.py)."""
+        _check(self.lib.ssb_local_nodal_flux(self.handle, dofs, neigh_int, _ptr(cell), _ptr(face), _ptr(inodal), m,
+                                             _stream(stream)))
 
     # -- set-up on the device --------------------------------------------------------------------
     def setup_cell_matrices(self, coords, neighbors, material, face_types, local_int, neigh_int, n, stream=None):

@@ -826,6 +826,26 @@ int ssb_local_nodal_bc(ssb_ctx* c, ssb_array_t dofs, ssb_array_t idofs, ssb_arra
   return c->ks->nodalBc(p, static_cast<cudaStream_t>(stream));
 }
 
+int ssb_local_nodal_flux(ssb_ctx* c, ssb_array_t dofs, ssb_array_t neigh_int, const long long* cell, const uint8_t* face,
+                         const void* inodal, long long m, void* stream) {
+  if (c == nullptr || m < 0 || c->equation != 0 || c->ks->nodalBc == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (m == 0) {
+    return 0;
+  }
+  NodalBcParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs); p.neighInt = conv(neigh_int);
+  if (!p.dofs.present() || !p.neighInt.present() || cell == nullptr || face == nullptr || inodal == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.cell = cell; p.face = face; p.kind = nullptr; p.analytical = inodal;
+  p.m = m;
+  p.ldg = c->ldq;
+  return c->ks->nodalBc(p, static_cast<cudaStream_t>(stream));
+}
+
 int ssb_setup_cell_matrices(ssb_ctx* c, const double* coords, const long long* neighbors, const double* material,
                             const uint8_t* face_types, ssb_array_t local_int, ssb_array_t neigh_int, long long n, void* stream) {
   if (c == nullptr || n < 0 || c->equation != 0) {

@@ -1,4 +1,4 @@
-// Nodal boundary conditions of the local integral: Dirichlet (easi boundary map) and FreeSurfaceGravity faces.
+// Nodal boundary conditions of the local integral: Dirichlet (easi boundary map), FreeSurfaceGravity and Analytical faces.
 //
 // Reference: Local::computeIntegral, src/Kernels/LinearCK/Local.cpp:157-252 (batched :350-455 through
 // DirichletBoundary::evaluateOnDevice, src/Kernels/LinearCK/DirichletBoundary.h:67-118), generated kernels
@@ -8,6 +8,7 @@
 //   INodal = N . Tinv^T                           rotated into the face-aligned frame
 //   Dirichlet (FaceType 4):          INodal(l, a) = sum_b map(a, b, l) INodal(l, b) + const(a, l)
 //   FreeSurfaceGravity (FaceType 2): INodal(l, 0..2) = 2 p - INodal(l, 0..2),  p = -rho g displacement(l)
+//   Analytical (FaceType 7):         INodal given by the caller (host callback, Local.cpp:409-452)
 //   Q_c   += project2nFaceTo3m_f . (INodal . AminusT_f)                                             [B x 9]
 // One warp per boundary face: lanes are the face nodes for the first three steps and the basis rows (lane, lane + 32)
 // for the last; the two dense operators come from lane-fastest tables (gen_nodal.py).  Boundary faces are a surface
@@ -23,12 +24,14 @@ struct NodalBcParams {
   ElemArray dofs, idofs, neighInt;
   const long long* cell;      // [m]
   const uint8_t* face;        // [m]
-  const uint8_t* kind;        // [m] FaceType: 4 = Dirichlet, 2 = FreeSurfaceGravity (others: face skipped)
+  const uint8_t* kind;        // [m] FaceType: 4 = Dirichlet, 2 = FreeSurfaceGravity (others: face skipped); NULL: every
+                              // face carries GIVEN nodal values (FaceType::Analytical, `analytical`)
   const void* tinv;           // [m][9][9] row-major Tinv(p, q)
   const void* easiMap;        // [m][9][9][B2] (a, b, l), Dirichlet faces
   const void* easiConst;      // [m][9][B2]
   const void* displacement;   // [m][B2], FreeSurfaceGravity faces
   const void* rhoG;           // [m] rho * g
+  const void* analytical;     // [m][9][B2] (a, l): time-integrated boundary values at the face nodes (Analytical faces)
   long long m;
   int ldg;
 };
@@ -45,12 +48,24 @@ __global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcPara
   if (i >= p.m) {
     return;
   }
-  const int kind = p.kind[i];
-  if (kind != 4 && kind != 2) {
+  constexpr int kAnalytical = 7;   // FaceType::Analytical
+  const int kind = p.kind != nullptr ? p.kind[i] : kAnalytical;
+  if (kind != 4 && kind != 2 && !(kind == kAnalytical && p.analytical != nullptr)) {
     return;   // warp-uniform
   }
   const long long c = p.cell[i];
   const int f = p.face[i];
+  R in[9];
+  if (kind == kAnalytical) {
+    // the boundary values at the face nodes are GIVEN (Local.cpp:409-452: the host evaluates the analytical solution at
+    // the nodes and integrates it over the time step, DirichletBoundary::evaluateTimeDependent; the device applies
+    // localFluxNodal to that scratch array)
+    const R* const given = static_cast<const R*>(p.analytical) + static_cast<size_t>(i) * 9 * B2 + lane;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+      in[a] = lane < B2 ? given[a * B2] : R(0);
+    }
+  } else {
   const R* const Ic = static_cast<const R*>(p.idofs.at(c));
   for (int q = 0; q < 9; ++q) {
     for (int k = lane; k < B; k += 32) {
@@ -78,7 +93,6 @@ __global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcPara
     }
   }
   // ---- INodal(l, p') = sum_q N(l, q) Tinv(p', q)
-  R in[9];
 #pragma unroll
   for (int pp = 0; pp < 9; ++pp) {
     R a = R(0);
@@ -88,8 +102,9 @@ __global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcPara
     }
     in[pp] = a;
   }
+  }
   // ---- the boundary condition at the node
-  if (lane < B2) {
+  if (lane < B2 && kind != kAnalytical) {
     if (kind == 4) {
       const R* map = static_cast<const R*>(p.easiMap) + static_cast<size_t>(i) * 81 * B2 + lane;
       const R* cst = static_cast<const R*>(p.easiConst) + static_cast<size_t>(i) * 9 * B2 + lane;

@@ -370,3 +370,33 @@ def test_local_nodal_boundary_conditions(gpu, order, dt):
     assert rel_l2(got, want) < t
     assert rel_l2(got - host["Q"], want - host["Q"]) < 10 * t
     assert np.unique(bc["cell"]).size < m      # at least one cell with two boundary faces
+
+
+@pytest.mark.parametrize("order,dt", [(4, np.float32), (6, np.float32), (6, np.float64)])
+def test_analytical_boundary_faces(gpu, order, dt):
+    """ssb_local_nodal_flux (FaceType::Analytical: host callback integrated over the time step by
+    seissol_b200.boundary.analytical_inodal, nodal flux on the device) against the oracle, which is pinned against the
+    reference's generated localFluxNodal (tests/test_oracle_dr.py)."""
+    from test_oracle_dr import nodal_bc_case, plane_wave_solution
+    from seissol_b200 import boundary
+    torch, api, proxy = gpu
+    n, m = 61, 90
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy)
+    rng = np.random.default_rng(34)
+    B2 = order * (order + 1) // 2
+    bc = nodal_bc_case(rng, n, m, B2, dt)
+    nodes = rng.uniform(-1, 1, (m, B2, 3))
+    inodal = boundary.analytical_inodal(plane_wave_solution, nodes, 0.1, 0.02, order, dtype=dt)     # [m, 9, B2]
+    tab64 = O.load_tables(order, np.float64)
+    want = O.local_nodal_flux(tab64, host["Q"].astype(np.float64), O.flux_dense(host["Aminus"]).astype(np.float64),
+                              bc["cell"], bc["face"], inodal.astype(np.float64).transpose(0, 2, 1))
+    dev = data.dofs.device
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    ctx.local_nodal_flux(api.strided(data.dofs), api.strided(data.neigh_int), d(bc["cell"]), d(bc["face"]), d(inodal), m)
+    torch.cuda.synchronize()
+    got = data.to_logical(data.dofs).astype(np.float64)
+    t = 5e-6 if dt == np.float32 else 1e-13
+    assert rel_l2(got, want) < t
+    assert rel_l2(got - host["Q"], want - host["Q"]) < 10 * t
+    lib = api.load_library()
+    assert lib.ssb_local_nodal_flux(ctx.handle, api.strided(data.dofs), api.strided(data.neigh_int), None, None, None, 3, None) == -1

@@ -106,3 +106,52 @@ def test_nodal_boundary_conditions_match_reference_library(cfg, order, dt):
     assert rel_l2(got, want) < tol
     assert rel_l2(got - d["Q"], want - d["Q"]) < 10 * tol
     assert np.linalg.norm(got - d["Q"]) > 1e-3 * np.linalg.norm(d["Q"])
+
+
+def plane_wave_solution(nodes, t):
+    """A smooth stand-in for physics::InitialField::evaluate: nine quantities at the nodes [B2, 3] at time t."""
+    k = np.array([0.7, -0.4, 0.9])
+    phase = nodes @ k - 1.3 * t
+    amp = np.linspace(0.5, 1.5, 9)
+    return np.sin(phase)[:, None] * amp[None, :] + 0.1 * t * np.cos(2 * phase)[:, None]
+
+
+@pytest.mark.parametrize("cfg,order,dt", [("elastic_o4_f32", 4, np.float32), ("elastic_o6_f64", 6, np.float64)])
+def test_analytical_boundary_faces_match_reference_library(cfg, order, dt):
+    """O.local_nodal_flux (FaceType::Analytical, Local.cpp:233-246) against the reference's generated localFluxNodal: the
+    reference library applies it to GIVEN nodal values when the easi map of a Dirichlet face is zero and the easi
+    constant holds the values.  The time integration of the callback (DirichletBoundary.h:121-165) is checked against
+    the exact integral of the test function."""
+    if not ref_lib.available(cfg):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    R = ref_lib.RefLib(cfg)
+    tab = O.load_tables(order, dt)
+    rng = np.random.default_rng(5)
+    n, m = 13, 19
+    B2 = order * (order + 1) // 2
+    d = O.proxy_data(order, n, dt, seed=4)
+    bc = nodal_bc_case(rng, n, m, B2, dt)
+    nodes = rng.uniform(-1, 1, (m, B2, 3))
+    inodal = O.analytical_inodal(plane_wave_solution, nodes, 0.25, 0.05, order).astype(dt)      # [m, B2, 9]
+    bc["kind"][:] = 4
+    bc["easiMap"][:] = 0
+    bc["easiConst"] = np.ascontiguousarray(inodal.transpose(0, 2, 1))
+    want = R.nodal_bc(d["Q"], np.zeros_like(d["Q"]), d["Aminus"], bc)
+    got = O.local_nodal_flux(tab, d["Q"], O.flux_dense(d["Aminus"]), bc["cell"], bc["face"], inodal)
+    tol = 100 * np.finfo(dt).eps
+    assert rel_l2(got, want) < tol
+    assert rel_l2(got - d["Q"], want - d["Q"]) < 10 * tol
+    # the quadrature of order O integrates the smooth callback to ~ (k dt)^(2 O)
+    fine = O.analytical_inodal(plane_wave_solution, nodes[:2], 0.25, 0.05, 12)
+    assert rel_l2(O.analytical_inodal(plane_wave_solution, nodes[:2], 0.25, 0.05, order), fine) < 1e-12
+
+
+def test_analytical_inodal_host_helper_equals_oracle():
+    """seissol_b200.boundary.analytical_inodal (product host code) = the oracle's restatement, in the ABI layout."""
+    from seissol_b200 import boundary
+    rng = np.random.default_rng(8)
+    nodes = rng.uniform(-1, 1, (7, 21, 3))
+    got = boundary.analytical_inodal(plane_wave_solution, nodes, 1.5, 0.01, 6)
+    want = O.analytical_inodal(plane_wave_solution, nodes, 1.5, 0.01, 6)
+    assert got.shape == (7, 9, 21)
+    assert rel_l2(got.transpose(0, 2, 1), want) < 1e-14
