@@ -54,6 +54,19 @@ def lit(v):
 class Emitter:
     def __init__(self):
         self.lines = []
+        self.consts = None     # constants of the function being emitted, in order of use (constant-table variant)
+        self.tab = None
+        self.tables = []       # (name, values) of all functions
+
+    def begin_table(self, name):
+        self.consts, self.tab = [], name
+
+    def end_table(self):
+        vals = self.consts + [0.0] * (len(self.consts) % 2)
+        self.tables.append((self.tab, vals))
+        n = len(vals) // 2
+        self.consts, self.tab = None, None
+        return n
 
     def w(self, s=""):
         self.lines.append(s)
@@ -63,11 +76,19 @@ class Emitter:
 
 
 def emit_acc(em, touched, name, i, coef, operand):
+    """One FMA per non-zero.  The matrix value is a literal (single precision: FFMA with an immediate operand) or, with
+    SSB_KTAB = 1 in double precision, half of a 16-byte pair fetched from the function's constant table in order of use
+    (DFMA has no immediate form: a literal costs two 32-bit moves per FMA, the table one 128-bit load per two FMAs)."""
+    j = len(em.consts)
+    em.consts.append(float(coef))
+    if j % 2 == 0:
+        em.w(f"    kp[{j // 2}] = kload<R>({em.tab}, {j // 2});")
+    c = f"ksel<R, {j % 2}>(kp[{j // 2}], {lit(coef)})"
     if touched is not None and i not in touched:
         touched.add(i)
-        em.w(f"    {name}[{i}] = pk_mulc({lit(coef)}, {operand});")
+        em.w(f"    {name}[{i}] = pk_mulc({c}, {operand});")
     else:
-        em.w(f"    {name}[{i}] = pk_fmac({lit(coef)}, {operand}, {name}[{i}]);")
+        em.w(f"    {name}[{i}] = pk_fmac({c}, {operand}, {name}[{i}]);")
 
 
 def finish_untouched(em, touched, n_local):
@@ -92,6 +113,9 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, accumulate):
     counts = []
     for h in (0, 1):
         em.w(f"  if constexpr (H == {h}) {{")
+        em.begin_table(f"ktab_{fname}_h{h}")
+        mark = len(em.lines)
+        em.w("KP_PLACEHOLDER")
         mine = rows_of(h, rows_out)
         touched = None if accumulate else set()
         nfma = 0
@@ -116,6 +140,7 @@ def gen_star_sweep(em, fname, mats, rows_in, rows_out, accumulate):
             em.w("    }")
         finish_untouched(em, touched, n_local)
         em.w("  }")
+        em.lines[mark] = f"    KPair<R> kp[{max(1, em.end_table())}];"
         counts.append(nfma)
     em.w("}")
     em.w()
@@ -132,6 +157,9 @@ def gen_spmv_src(em, fname, m, accumulate=False):
     counts = []
     for h in (0, 1):
         em.w(f"  if constexpr (H == {h}) {{")
+        em.begin_table(f"ktab_{fname}_h{h}")
+        mark = len(em.lines)
+        em.w("KP_PLACEHOLDER")
         mine = rows_of(h, rows)
         touched = None if accumulate else set()
         nfma = 0
@@ -154,6 +182,7 @@ def gen_spmv_src(em, fname, m, accumulate=False):
             em.w("    }")
         finish_untouched(em, touched, n_local)
         em.w("  }")
+        em.lines[mark] = f"    KPair<R> kp[{max(1, em.end_table())}];"
         counts.append(nfma)
     em.w("}")
     em.w()
@@ -171,6 +200,9 @@ def gen_spmv_chunks(em, fname, m):
     counts = []
     for h in (0, 1):
         em.w(f"  if constexpr (H == {h}) {{")
+        em.begin_table(f"ktab_{fname}_h{h}")
+        mark = len(em.lines)
+        em.w("KP_PLACEHOLDER")
         mine = rows_of(h, rows)
         nfma = 0
         for c in range(pad4(cols) // 4):
@@ -185,6 +217,7 @@ def gen_spmv_chunks(em, fname, m):
                         nfma += 1
             em.w("    }")
         em.w("  }")
+        em.lines[mark] = f"    KPair<R> kp[{max(1, em.end_table())}];"
         counts.append(nfma)
     em.w("}")
     em.w()
@@ -218,6 +251,7 @@ def generate(order):
     em.w(f"constexpr int kBP = {pad4(B)};")
     em.w(f"constexpr int kB2P = {pad4(B2)};")
     stats = {}
+    head_end = len(em.lines)
     for d in range(1, order):
         rin, rout = nb3(order - d + 1), nb3(order - d)
         mats = [kdmt[j][:rout, :rin] for j in range(3)]
@@ -243,6 +277,12 @@ def generate(order):
              f" c.template finish<{n}>({d}, out); }}")
     em.w("}")
     em.w()
+    # constant tables of the functions above (used by the SSB_KTAB = 1 build only; unused tables are dropped)
+    tabs = ["// matrix values in order of use, one table per function and row half (constant-table variant, SSB_KTAB = 1)"]
+    for name, vals in em.tables:
+        body = ", ".join(repr(v) for v in vals) if vals else "0.0, 0.0"
+        tabs.append(f"static __device__ __align__(16) const double {name}[{max(2, len(vals))}] = {{{body}}};")
+    em.lines[head_end:head_end] = tabs
     em.w("// FMA instruction counts per thread (half column), H = 0 / 1:")
     for k, v in stats.items():
         em.w(f"//   {k}: {v[0]} / {v[1]}")

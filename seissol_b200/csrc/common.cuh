@@ -268,6 +268,34 @@ __device__ __forceinline__ void st2lane(double* p, int v, double2 a, double2 b) 
   *reinterpret_cast<double2*>(p) = v == 0 ? make_double2(a.x, b.x) : make_double2(a.y, b.y);
 }
 
+// Matrix values of the generated operator code (generation 4): literals, or -- double precision with SSB_KTAB = 1 -- pairs
+// streamed from a per-function constant table in global memory (L1-resident, every lane reads the same 16 bytes):
+// one LDG.128 per two DFMAs instead of two 32-bit moves per DFMA (codegen/gen_ops4.py::emit_acc).
+#ifndef SSB_KTAB
+#define SSB_KTAB 0
+#endif
+template <typename R> struct KPair {};
+#if SSB_KTAB == 1
+template <> struct KPair<double> { double x, y; };
+#endif
+template <typename R> __device__ __forceinline__ KPair<R> kload(const double* tab, int j) {
+  KPair<R> k;
+#if SSB_KTAB == 1
+  if constexpr (sizeof(R) == 8) {
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(k.x), "=d"(k.y) : "l"(tab + 2 * j));
+  }
+#endif
+  return k;
+}
+template <typename R, int I> __device__ __forceinline__ R ksel(const KPair<R>& k, R literal) {
+#if SSB_KTAB == 1
+  if constexpr (sizeof(R) == 8) {
+    return I == 0 ? k.x : k.y;
+  }
+#endif
+  return literal;
+}
+
 // Operand sources of the generated sparse mat-vec code: a lane-interleaved column, or V
 // separate per-element columns (TMA landing zones) packed on the fly.
 template <typename R> struct SrcPk {

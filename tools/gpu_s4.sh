@@ -16,6 +16,20 @@ pd2)
 rsfast)
   timeout 600 python -m pytest tests/test_gpu_dr.py -m gpu -x -q -k "n_steps" > $out/pytest_dr.log 2>&1; echo "exit $?" >> $out/pytest_dr.log
   timeout 300 python bench.py --config dr_rsfvw_fast --steps 5 --no-cpu > $out/bench_dr_rsfvw_fast.json 2> $out/bench_dr_rsfvw_fast.err ;;
+kt)
+  for v in $KTV; do
+    SSB_LIB=$L/libseissol_b200_$v.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "float64" > $out/pytest_$v.log 2>&1; echo "exit $?" >> $out/pytest_$v.log
+    SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_$v.txt 2>&1
+    SSB_ADER_GEN=4 SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_${v}_ader4.txt 2>&1
+  done ;;
+ana)
+  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "analytical or nodal" > $out/pytest_ana.log 2>&1; echo "exit $?" >> $out/pytest_ana.log
+  SSB_KGEN=3 SSB_KGEN5=1 timeout 300 $QB > $out/qb_f64_g3_local5.txt 2>&1
+  SSB_KGEN=3 SSB_KGEN5=3 timeout 300 $QB > $out/qb_f64_g3_both5.txt 2>&1 ;;
+lts2)
+  (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 5 --warmup 3 > $out/bench_lts2.json 2> $out/bench_lts2.err) 2> $out/bench_lts2.time
+  (time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 2 --warmup 1 --impl reference > $out/bench_ref2.json 2> $out/bench_ref2.err) 2> $out/bench_ref2.time
+  timeout 600 python -m pytest tests/test_lts.py tests/test_host_cpp.py -m gpu -x -q > $out/pytest_lts2.log 2>&1; echo "exit $?" >> $out/pytest_lts2.log ;;
 esac
 done
-for f in $out/*.log $out/*.txt $out/*.json; do echo "=== $f"; tail -c 1200 $f; done
+for f in $out/*.log $out/*.txt $out/*.json $out/*.time; do echo "=== $f"; tail -c 1200 $f; done
