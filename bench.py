@@ -155,8 +155,8 @@ class ElasticWorkload(Workload):
         prec = "single" if self.real == 4 else "double"
         self.name = (f"proxy elastic ORDER={self.order} {prec} precision kernel=all, {self.cells} elements with the proxy's random "
                      f"fake topology (BASELINE.json {cfg['baseline']})")
-        self.kernel_names = {"ader": "k_local<ader>", "localwoader": "k_local5 (volume + local flux, writes face projections)"
-                             if self.k.faceproj else "k_local<localwoader>",
+        local_fp = ("k_local5" if self.real == 4 else "k_local4") + " (volume + local flux, writes face projections)"
+        self.kernel_names = {"ader": "k_local<ader>", "localwoader": local_fp if self.k.faceproj else "k_local<localwoader>",
                              "neigh": "k_neigh_fp (face projections)" if self.k.faceproj else "k_neigh"}
 
     def segments(self):

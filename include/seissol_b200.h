@@ -290,6 +290,18 @@ int ssb_local_nodal_bc(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t idofs, ssb_ar
 int ssb_local_nodal_flux(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t neigh_int, const long long* cell,
                          const uint8_t* face, const void* inodal, long long m, void* stream);
 
+/* Volume part of the energy output (EnergyOutput::computeVolumeEnergies, src/ResultWriter/EnergyOutput.cpp:347-486) for n
+ * elements: kinetic energy 0.5 rho |v|^2, elastic strain energy 0.5 sigma : eps(sigma), acoustic energy p^2 / (2 K) of
+ * elements with mu = 0, total momentum rho v, integrated over every element.  The reference evaluates Q at (O+1)^3
+ * quadrature points per element; the integrands are quadratic in the orthogonal modal basis, so the kernel takes the same
+ * integrals from the modal coefficients in one streaming pass over Q (sums in double).  volume [n] and material [n][3] =
+ * lambda, mu, rho are DEVICE arrays of doubles.  out: DEVICE double[8], ACCUMULATED (zero it first): [0] elastic kinetic
+ * energy, [1] elastic energy, [2] acoustic kinetic energy, [3] acoustic energy, [4..6] momentum x, y, z, [7] unused (the
+ * gravitational energy of free-surface-gravity faces and the plastic moment are not covered; the fault's frictional
+ * energy is an output of ssb_friction_*).  Ghost / duplicate cells are the caller's to leave out, as :405-408 does. */
+int ssb_volume_energies(ssb_ctx* ctx, ssb_array_t dofs, const double* volume, const double* material, long long n,
+                        double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Set-up on the device (elastic): the per-element and per-fault-face matrices the entry points above consume, from
  * vertex coordinates and material parameters; all inputs are DEVICE arrays of doubles, results are stored in the

@@ -246,6 +246,70 @@ def local_nodal_flux(tab, Q, Aminus, cell, face, inodal):
     return out
 
 
+def tetrahedron_quadrature(n):
+    """seissol::quadrature::TetrahedronQuadrature (src/Numerical/Quadrature.h:156-200): conical product of n-point
+    Gauss-Jacobi rules with weights (1-x)^2, (1-x), 1 mapped to [0, 1].  Returns points [n^3, 3], weights [n^3]."""
+    from scipy.special import roots_jacobi
+    p0, w0 = roots_jacobi(n, 2, 0)
+    p1, w1 = roots_jacobi(n, 1, 0)
+    p2, w2 = roots_jacobi(n, 0, 0)
+    p0, p1, p2 = 0.5 * p0 + 0.5, 0.5 * p1 + 0.5, 0.5 * p2 + 0.5
+    w0, w1, w2 = 0.125 * w0, 0.25 * w1, 0.5 * w2
+    i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    pts = np.stack([p0[i], p1[j] * (1 - p0[i]), p2[k] * (1 - p1[j]) * (1 - p0[i])], -1)
+    return pts, w0[i] * w1[j] * w2[k]
+
+
+def dubiner_basis(order, pts):
+    """Basis functions of the reference tetrahedron at pts [m, 3] -> [m, B] (src/Numerical/Functions.cpp:136-148,
+    ordering src/Numerical/BasisFunction.h:135-143): the evalAtQP matrix of the energy output when pts are the
+    quadrature points."""
+    from scipy.special import eval_jacobi
+    xi, eta, zeta = pts[:, 0], pts[:, 1], pts[:, 2]
+    r, s, t = 2 * xi - 1 + eta + zeta, 2 * eta - 1 + zeta, 2 * zeta - 1
+    st, th = 1 - eta - zeta, 1 - zeta
+
+    def sfj(n, a, x, y):
+        yy = np.where(np.abs(y) < 1e-300, 1e-300, y)
+        return yy ** n * eval_jacobi(n, a, 0, x / yy)
+
+    idx = [(o - j - k, j, k) for o in range(order) for k in range(o + 1) for j in range(o - k + 1)]
+    return np.stack([sfj(i, 0, r, st) * sfj(j, 2 * i + 1, s, th) * eval_jacobi(k, 2 * i + 2 * j + 2, 0, t) for i, j, k in idx], -1)
+
+
+def volume_energies(order, Q, volume, material):
+    """EnergyOutput::computeVolumeEnergies (src/ResultWriter/EnergyOutput.cpp:347-486) without the gravitational and
+    plastic parts: Q [n, B, 9] evaluated at the (O+1)^3 quadrature points (kernel::evalAtQP), per point
+    kinetic 0.5 rho |v|^2, elastic 0.5 sigma : eps, acoustic p^2 / (2 lambda) for mu = 0, momentum rho v, weight 6 |V| w.
+    material [n, 3] = lambda, mu, rho.  Returns [elasticKinetic, elastic, acousticKinetic, acoustic, mx, my, mz, 0]."""
+    pts, w = tetrahedron_quadrature(order + 1)
+    phi = dubiner_basis(order, pts)
+    out = np.zeros(8)
+    lookup = [[0, 3, 5], [3, 1, 4], [5, 4, 2]]
+    for c in range(Q.shape[0]):
+        num = phi @ Q[c].astype(np.float64)            # [qp, 9]
+        cw = 6.0 * volume[c] * w
+        lam, mu, rho = material[c]
+        kin = 0.5 * rho * (num[:, 6] ** 2 + num[:, 7] ** 2 + num[:, 8] ** 2)
+        if abs(mu) < 10e-14:
+            out[3] += np.sum(cw * num[:, 0] ** 2 / (2 * lam))
+            out[2] += np.sum(cw * kin)
+            continue
+        out[0] += np.sum(cw * kin)
+        out[4:7] += rho * (cw @ num[:, 6:9])
+        tr = num[:, 0] + num[:, 1] + num[:, 2]
+        factor = -lam / (2.0 * mu * (3.0 * lam + 2.0 * mu))
+        e = np.zeros(len(w))
+        for i in range(3):
+            for j in range(3):
+                sij = num[:, lookup[i][j]]
+                strain = sij / (2.0 * mu) + (factor * tr if i == j else 0.0)
+                e += sij * strain
+        out[1] += np.sum(cw * 0.5 * e)
+    return out
+
+
 def dr_interpolate(tab, ders_plus, ders_minus, tinvT, face_info, coeffs):
     """DynamicRupture::spaceTimeInterpolation (src/Kernels/DynamicRupture.cpp:57-108):
     for each time point s: Q±(t_s) = sum_d coeffs[s,d] dQ±(d);

@@ -77,6 +77,7 @@ struct KernelSet {
   int (*accumulate)(const AccumulateParams&, cudaStream_t);
   int (*taylorFp)(const TaylorParams&, cudaStream_t);   // Taylor sum + face projection (full-column units only)
   int (*nodalBc)(const struct NodalBcParams&, cudaStream_t);   // nodal boundary conditions (full-column units only)
+  int (*volumeEnergies)(const struct VolumeEnergyParams&, cudaStream_t);   // energy output (full-column units only)
 };
 
 struct NodalBcParams;

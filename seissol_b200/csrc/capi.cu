@@ -846,6 +846,26 @@ int ssb_local_nodal_flux(ssb_ctx* c, ssb_array_t dofs, ssb_array_t neigh_int, co
   return c->ks->nodalBc(p, static_cast<cudaStream_t>(stream));
 }
 
+int ssb_volume_energies(ssb_ctx* c, ssb_array_t dofs, const double* volume, const double* material, long long n,
+                        double* out, void* stream) {
+  if (c == nullptr || n < 0 || c->equation != 0 || c->ks->volumeEnergies == nullptr) {
+    return SSB_EINVAL;
+  }
+  if (n == 0) {
+    return 0;
+  }
+  VolumeEnergyParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.dofs = conv(dofs);
+  if (!p.dofs.present() || volume == nullptr || material == nullptr || out == nullptr) {
+    return SSB_EINVAL;
+  }
+  p.volume = volume; p.material = material; p.out = out;
+  p.n = n;
+  p.ldg = c->ldq;
+  return c->ks->volumeEnergies(p, static_cast<cudaStream_t>(stream));
+}
+
 int ssb_setup_cell_matrices(ssb_ctx* c, const double* coords, const long long* neighbors, const double* material,
                             const uint8_t* face_types, ssb_array_t local_int, ssb_array_t neigh_int, long long n, void* stream) {
   if (c == nullptr || n < 0 || c->equation != 0) {

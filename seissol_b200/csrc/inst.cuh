@@ -346,6 +346,7 @@ struct GenNodal {
   __device__ __forceinline__ static const R* nodalV() { return SSB_CAT(gen_nodal_o, SSB_ORDER)::nodalV<R>(); }
   template <typename R>
   __device__ __forceinline__ static const R* nodalP() { return SSB_CAT(gen_nodal_o, SSB_ORDER)::nodalP<R>(); }
+  __device__ __forceinline__ static const double* massDiag() { return SSB_CAT(gen_nodal_o, SSB_ORDER)::massDiag(); }
 };
 
 int nodalBcEntry(const NodalBcParams& p, cudaStream_t stream) {
@@ -357,8 +358,21 @@ int nodalBcEntry(const NodalBcParams& p, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
+int volumeEnergiesEntry(const VolumeEnergyParams& p, cudaStream_t stream) {
+  if (p.n <= 0) {
+    return 0;
+  }
+  long long blocks = (p.n + 7) / 8;
+  const long long resident = 8LL * smCount();   // 64 warps per SM stream the elements
+  if (blocks > resident) {
+    blocks = resident;
+  }
+  k_volume_energies<Real, Gen, GenNodal><<<unsigned(blocks), 256, 0, stream>>>(p);
+  return int(cudaGetLastError());
+}
+
 const KernelSet kSet = {Gen::kOrder, int(sizeof(Real)), Gen::kB, Gen::kBP, EL * VL, EN * VL, localEntry, neighEntry, taylorEntry, accumulateEntry, taylorFpEntry,
-                        nodalBcEntry};
+                        nodalBcEntry, volumeEnergiesEntry};
 
 }  // namespace
 

@@ -179,4 +179,90 @@ __global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcPara
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Volume energies of the energy output: EnergyOutput::computeVolumeEnergies (src/ResultWriter/EnergyOutput.cpp:347-486).
+// The reference evaluates Q at (O+1)^3 quadrature points of every element (kernel::evalAtQP) and sums
+//   kinetic 0.5 rho |v|^2,  elastic 0.5 sigma : eps(sigma),  acoustic p^2 / (2 K) (elements with mu = 0),  momentum rho v
+// with weights 6 |V| w_qp.  All integrands are products of two expansions in the ORTHOGONAL modal basis, and the quadrature
+// is exact for them (degree 2 (O - 1) <= 2 (O + 1) - 1), so the same integrals are
+//   int f g = 6 |V| sum_k M_kk f_k g_k,        int f = 6 |V| M_00 f_0   (phi_0 = 1)
+// evaluated here straight from the modal coefficients: one pass over Q (HBM-bound), one warp per element, sums in double.
+// out[8] (accumulated with atomic adds, the caller zeroes it): elastic kinetic, elastic, acoustic kinetic, acoustic,
+// momentum x / y / z, out[7] unused (the gravitational energy needs the face displacements of the boundary faces).
+struct VolumeEnergyParams {
+  ElemArray dofs;
+  const double* volume;     // [n]
+  const double* material;   // [n][3] lambda, mu, rho
+  double* out;              // [8]
+  long long n;
+  int ldg;
+};
+
+template <typename R, typename G, typename GN>
+__global__ void __launch_bounds__(256) k_volume_energies(const VolumeEnergyParams p) {
+  constexpr int B = G::kB;
+  __shared__ double sAcc[8][8];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long nWarps = static_cast<long long>(gridDim.x) * 8;
+  double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+  const double* const mass = GN::massDiag();
+  for (long long el = static_cast<long long>(blockIdx.x) * 8 + warp; el < p.n; el += nWarps) {
+    const R* const Q = static_cast<const R*>(p.dofs.at(el));
+    double kin = 0, sq = 0, tr = 0, pp = 0;
+    for (int k = lane; k < B; k += 32) {
+      R q[9];
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        q[a] = Q[a * p.ldg + k];
+      }
+      const double m = mass[k];
+      const double xx = q[0], yy = q[1], zz = q[2], xy = q[3], yz = q[4], xz = q[5];
+      const double u = q[6], v = q[7], w = q[8];
+      kin += m * (u * u + v * v + w * w);
+      sq += m * (xx * xx + yy * yy + zz * zz + 2.0 * (xy * xy + yz * yz + xz * xz));
+      tr += m * (xx + yy + zz) * (xx + yy + zz);
+      pp += m * xx * xx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kin += __shfl_xor_sync(0xffffffffu, kin, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      tr += __shfl_xor_sync(0xffffffffu, tr, o);
+      pp += __shfl_xor_sync(0xffffffffu, pp, o);
+    }
+    if (lane == 0) {
+      const double jac = 6.0 * p.volume[el];
+      const double lambda = p.material[3 * el], mu = p.material[3 * el + 1], rho = p.material[3 * el + 2];
+      if (fabs(mu) < 10e-14) {   // acoustic element (EnergyOutput.cpp:443-450)
+        tot[2] += jac * 0.5 * rho * kin;
+        tot[3] += jac * pp / (2.0 * lambda);
+      } else {
+        tot[0] += jac * 0.5 * rho * kin;
+        const double factor = -lambda / (2.0 * mu * (3.0 * lambda + 2.0 * mu));
+        tot[1] += jac * 0.5 * (sq / (2.0 * mu) + factor * tr);
+        const double m0 = jac * mass[0] * rho;
+        tot[4] += m0 * static_cast<double>(Q[6 * p.ldg]);
+        tot[5] += m0 * static_cast<double>(Q[7 * p.ldg]);
+        tot[6] += m0 * static_cast<double>(Q[8 * p.ldg]);
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      sAcc[warp][i] = tot[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double s = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) {
+      s += sAcc[wv][threadIdx.x];
+    }
+    atomicAdd(p.out + threadIdx.x, s);
+  }
+}
+
 }  // namespace ssb

@@ -400,3 +400,30 @@ def test_analytical_boundary_faces(gpu, order, dt):
     assert rel_l2(got - host["Q"], want - host["Q"]) < 10 * t
     lib = api.load_library()
     assert lib.ssb_local_nodal_flux(ctx.handle, api.strided(data.dofs), api.strided(data.neigh_int), None, None, None, 3, None) == -1
+
+
+@pytest.mark.parametrize("order,dt", [(4, np.float32), (6, np.float32), (6, np.float64)])
+def test_volume_energies(gpu, order, dt):
+    """ssb_volume_energies (modal integrals, one streaming pass) against the oracle's restatement of
+    EnergyOutput::computeVolumeEnergies (evaluation at the (O+1)^3 quadrature points); elastic and acoustic elements,
+    ragged count, accumulation over two calls."""
+    torch, api, proxy = gpu
+    n = 1237
+    ctx, host, data, tab, c = make(order, dt, n, api, proxy)
+    rng = np.random.default_rng(12)
+    vol = rng.uniform(0.5, 2.0, n)
+    mat = np.stack([rng.uniform(1.0, 3.0, n), rng.uniform(0.5, 2.0, n), rng.uniform(1.0, 3.0, n)], -1)
+    mat[::7, 1] = 0.0                                   # acoustic elements
+    want = O.volume_energies(order, host["Q"].astype(np.float64), vol, mat)
+    dev = data.dofs.device
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)  # noqa: E731
+    ctx.volume_energies(api.strided(data.dofs), d(vol), d(mat), n, out)
+    got = out.cpu().numpy()
+    t = 2e-6 if dt == np.float32 else 1e-12
+    assert np.all(np.abs(got[:7] - want[:7]) <= t * np.abs(want[:7]).max()), (got, want)
+    assert want[3] > 0 and want[0] > 0
+    ctx.volume_energies(api.strided(data.dofs), d(vol), d(mat), n, out)          # accumulates
+    assert np.allclose(out.cpu().numpy()[:7], 2 * got[:7], rtol=1e-12)
+    lib = api.load_library()
+    assert lib.ssb_volume_energies(ctx.handle, api.strided(data.dofs), None, None, 5, None, None) == -1

@@ -92,3 +92,28 @@ def test_linearity_and_zero_star():
     assert rel_l2(b, 2.5 * a) < 1e-14
     z = O.ader(tab, d["Q"], np.zeros_like(star), c)
     assert rel_l2(z, c[0] * d["Q"]) < 1e-15
+
+
+def test_energy_output_quadrature_matches_the_reference_mass_matrix():
+    """The quadrature + basis of the energy-output oracle (O.volume_energies) reproduce the reference's modal mass
+    matrix M3 (codegen/matrices, tables o*.npz), which is what the CUDA kernel integrates with; and the energies of a
+    constant state have their closed form."""
+    for order in (4, 6):
+        tab = O.load_tables(order, np.float64)
+        pts, w = O.tetrahedron_quadrature(order + 1)
+        assert abs(w.sum() - 1.0 / 6.0) < 1e-14
+        phi = O.dubiner_basis(order, pts)
+        mass = np.einsum("m,mk,ml->kl", w, phi, phi)
+        assert np.abs(mass - tab["M3"]).max() < 1e-13
+    B = 56
+    Q = np.zeros((2, B, 9))
+    Q[:, 0, 6:9] = [2.0, -1.0, 0.5]       # constant velocity (phi_0 = 1)
+    Q[:, 0, 0:3] = 3.0                    # isotropic stress
+    vol = np.array([0.25, 0.5])
+    mat = np.array([[2.0, 1.0, 3.0], [4.0, 0.0, 2.0]])   # second element acoustic
+    e = O.volume_energies(6, Q, vol, mat)
+    assert abs(e[0] - 0.25 * 0.5 * 3.0 * 5.25) < 1e-13
+    assert abs(e[1] - 0.25 * 0.5 * 27.0 / (3 * 2.0 + 2 * 1.0)) < 1e-13     # 0.5 tr(s)^2 / (3 (3 lambda + 2 mu)) * 3 ... = 0.5 * 27 / 8
+    assert abs(e[2] - 0.5 * 0.5 * 2.0 * 5.25) < 1e-13
+    assert abs(e[3] - 0.5 * 9.0 / 8.0) < 1e-13
+    assert np.allclose(e[4:7], 0.25 * 3.0 * np.array([2.0, -1.0, 0.5]), atol=1e-13)

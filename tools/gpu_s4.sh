@@ -22,6 +22,12 @@ kt)
     SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_$v.txt 2>&1
     SSB_ADER_GEN=4 SSB_LIB=$L/libseissol_b200_$v.so timeout 300 $QB > $out/qb_f64_${v}_ader4.txt 2>&1
   done ;;
+final)
+  timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > $out/pytest.log 2>&1; echo "exit $?" >> $out/pytest.log
+  timeout 600 python bench.py > $out/bench_elastic_f32.json 2> $out/bench_elastic_f32.err
+  for c in elastic_f64 o4 visco dr_lsw dr_rsfvw dr_rsfvw_fast; do
+    timeout 600 python bench.py --config $c --steps 10 > $out/bench_$c.json 2> $out/bench_$c.err
+  done ;;
 ana)
   timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "analytical or nodal" > $out/pytest_ana.log 2>&1; echo "exit $?" >> $out/pytest_ana.log
   SSB_KGEN=3 SSB_KGEN5=1 timeout 300 $QB > $out/qb_f64_g3_local5.txt 2>&1
