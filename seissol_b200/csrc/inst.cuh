@@ -362,7 +362,8 @@ int volumeEnergiesEntry(const VolumeEnergyParams& p, cudaStream_t stream) {
   if (p.n <= 0) {
     return 0;
   }
-  long long blocks = (p.n + 7) / 8;
+  constexpr int perBlock = 8 * (sizeof(Real) == 4 ? 2 : 1);   // elements per CTA and iteration
+  long long blocks = (p.n + perBlock - 1) / perBlock;
   const long long resident = 8LL * smCount();   // 64 warps per SM stream the elements
   if (blocks > resident) {
     blocks = resident;

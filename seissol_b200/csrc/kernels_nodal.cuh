@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(32 * WARPS) k_local_nodal_bc(const NodalBcPara
 // with weights 6 |V| w_qp.  All integrands are products of two expansions in the ORTHOGONAL modal basis, and the quadrature
 // is exact for them (degree 2 (O - 1) <= 2 (O + 1) - 1), so the same integrals are
 //   int f g = 6 |V| sum_k M_kk f_k g_k,        int f = 6 |V| M_00 f_0   (phi_0 = 1)
-// evaluated here straight from the modal coefficients: one pass over Q (HBM-bound), one warp per element, sums in double.
+// evaluated here straight from the modal coefficients: one pass over Q (HBM-bound), 16 (float) / 32 (double) lanes per
+// element with one 128-bit load per lane and quantity, sums in double.
 // out[8] (accumulated with atomic adds, the caller zeroes it): elastic kinetic, elastic, acoustic kinetic, acoustic,
 // momentum x / y / z, out[7] unused (the gravitational energy needs the face displacements of the boundary faces).
 struct VolumeEnergyParams {
@@ -201,37 +202,67 @@ struct VolumeEnergyParams {
 template <typename R, typename G, typename GN>
 __global__ void __launch_bounds__(256) k_volume_energies(const VolumeEnergyParams p) {
   constexpr int B = G::kB;
+  constexpr int W = 16 / int(sizeof(R));            // reals per 128-bit load
+  constexpr int L = sizeof(R) == 4 ? 16 : 32;       // lanes per element: L * W rows >= B (B <= 56)
+  constexpr int EPW = 32 / L;                       // elements per warp and iteration
+  static_assert(L * W >= B, "one 128-bit load per lane and quantity covers a column");
   __shared__ double sAcc[8][8];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const long long nWarps = static_cast<long long>(gridDim.x) * 8;
-  double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-  const double* const mass = GN::massDiag();
-  for (long long el = static_cast<long long>(blockIdx.x) * 8 + warp; el < p.n; el += nWarps) {
-    const R* const Q = static_cast<const R*>(p.dofs.at(el));
-    double kin = 0, sq = 0, tr = 0, pp = 0;
-    for (int k = lane; k < B; k += 32) {
-      R q[9];
+  const int sub = lane / L, sl = lane % L;
+  const bool rows = sl * W < B;
+  double mass[W];
 #pragma unroll
-      for (int a = 0; a < 9; ++a) {
-        q[a] = Q[a * p.ldg + k];
+  for (int i = 0; i < W; ++i) {
+    mass[i] = sl * W + i < B ? GN::massDiag()[sl * W + i] : 0.0;
+  }
+  const double mass0 = GN::massDiag()[0];
+  double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long stride = static_cast<long long>(gridDim.x) * 8 * EPW;
+  for (long long base = (static_cast<long long>(blockIdx.x) * 8 + warp) * EPW; base < p.n; base += stride) {
+    const long long el = base + sub;
+    const bool valid = el < p.n;
+    const R* const Q = valid ? static_cast<const R*>(p.dofs.at(el)) : nullptr;
+    R q[9][W];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+      if (valid && rows) {
+        if constexpr (sizeof(R) == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(Q + a * p.ldg + sl * W);
+          q[a][0] = t.x; q[a][1] = t.y; q[a][2] = t.z; q[a][3] = t.w;
+        } else {
+          const double2 t = *reinterpret_cast<const double2*>(Q + a * p.ldg + sl * W);
+          q[a][0] = t.x; q[a][1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          q[a][i] = R(0);
+        }
       }
-      const double m = mass[k];
-      const double xx = q[0], yy = q[1], zz = q[2], xy = q[3], yz = q[4], xz = q[5];
-      const double u = q[6], v = q[7], w = q[8];
-      kin += m * (u * u + v * v + w * w);
-      sq += m * (xx * xx + yy * yy + zz * zz + 2.0 * (xy * xy + yz * yz + xz * xz));
-      tr += m * (xx + yy + zz) * (xx + yy + zz);
-      pp += m * xx * xx;
+    }
+    double kin = 0, sq = 0, tr = 0, pp = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      // the point values and their products are `real` in the reference too (EnergyOutput.cpp:435-438, :463-481); the
+      // sums are double.  In single precision this keeps the kernel on the HBM side of the conversion / DFMA rates.
+      const double m = mass[i];
+      const R xx = q[0][i], yy = q[1][i], zz = q[2][i], xy = q[3][i], yz = q[4][i], xz = q[5][i];
+      const R u = q[6][i], v = q[7][i], w = q[8][i];
+      const R trace = xx + yy + zz;
+      kin += m * static_cast<double>(u * u + v * v + w * w);
+      sq += m * static_cast<double>(xx * xx + yy * yy + zz * zz + R(2) * (xy * xy + yz * yz + xz * xz));
+      tr += m * static_cast<double>(trace * trace);
+      pp += m * static_cast<double>(xx * xx);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = L / 2; o > 0; o >>= 1) {   // stays inside the L-lane group of the element
       kin += __shfl_xor_sync(0xffffffffu, kin, o);
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
       tr += __shfl_xor_sync(0xffffffffu, tr, o);
       pp += __shfl_xor_sync(0xffffffffu, pp, o);
     }
-    if (lane == 0) {
+    if (sl == 0 && valid) {
       const double jac = 6.0 * p.volume[el];
       const double lambda = p.material[3 * el], mu = p.material[3 * el + 1], rho = p.material[3 * el + 2];
       if (fabs(mu) < 10e-14) {   // acoustic element (EnergyOutput.cpp:443-450)
@@ -241,11 +272,18 @@ __global__ void __launch_bounds__(256) k_volume_energies(const VolumeEnergyParam
         tot[0] += jac * 0.5 * rho * kin;
         const double factor = -lambda / (2.0 * mu * (3.0 * lambda + 2.0 * mu));
         tot[1] += jac * 0.5 * (sq / (2.0 * mu) + factor * tr);
-        const double m0 = jac * mass[0] * rho;
-        tot[4] += m0 * static_cast<double>(Q[6 * p.ldg]);
-        tot[5] += m0 * static_cast<double>(Q[7 * p.ldg]);
-        tot[6] += m0 * static_cast<double>(Q[8 * p.ldg]);
+        const double m0 = jac * mass0 * rho;   // row 0 of the columns 6..8 is element 0 of this lane's loads
+        tot[4] += m0 * static_cast<double>(q[6][0]);
+        tot[5] += m0 * static_cast<double>(q[7][0]);
+        tot[6] += m0 * static_cast<double>(q[8][0]);
       }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot[i] += __shfl_xor_sync(0xffffffffu, tot[i], o);
     }
   }
   if (lane == 0) {

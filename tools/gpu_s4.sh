@@ -28,6 +28,14 @@ final)
   for c in elastic_f64 o4 visco dr_lsw dr_rsfvw dr_rsfvw_fast; do
     timeout 600 python bench.py --config $c --steps 10 > $out/bench_$c.json 2> $out/bench_$c.err
   done ;;
+energy)
+  timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_host_cpp.py -m gpu -x -q > $out/pytest_energy.log 2>&1; echo "exit $?" >> $out/pytest_energy.log
+  timeout 300 python tools/quick_bench_stream.py > $out/qb_stream.txt 2>&1 ;;
+energy2)
+  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "volume_energies" > $out/pytest_energy.log 2>&1; echo "exit $?" >> $out/pytest_energy.log
+  timeout 300 python tools/quick_bench_stream.py > $out/qb_stream.txt 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu > $out/launches_bench.log 2>&1 ;;
 ana)
   timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "analytical or nodal" > $out/pytest_ana.log 2>&1; echo "exit $?" >> $out/pytest_ana.log
   SSB_KGEN=3 SSB_KGEN5=1 timeout 300 $QB > $out/qb_f64_g3_local5.txt 2>&1

@@ -39,6 +39,12 @@ def main():
         t = timeit(lambda: ctx.lts_accumulate(api.strided(buffers), api.strided(idofs), False, n))
         by = 3 * 504 * real * n
         print(f"real {real}: lts_accumulate  {t * 1e3:7.3f} ms  {n / t / 1e6:8.1f} Melem/s  {by / t / 1e9:8.1f} GB/s(alg)")
+        vol = torch.rand(n, device="cuda", dtype=torch.float64) + 0.5
+        mat = torch.rand((n, 3), device="cuda", dtype=torch.float64) + 1.0
+        out = torch.zeros(8, device="cuda", dtype=torch.float64)
+        t = timeit(lambda: ctx.volume_energies(api.strided(idofs), vol, mat, n, out))
+        by = (504 * real + 4 * 8) * n
+        print(f"real {real}: volume_energies {t * 1e3:7.3f} ms  {n / t / 1e6:8.1f} Melem/s  {by / t / 1e9:8.1f} GB/s(alg)")
 
 
 if __name__ == "__main__":
