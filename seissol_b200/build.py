@@ -91,6 +91,13 @@ def build(verbose=True, force=False, extra_flags=(), variant=None, variant_sourc
             return os.path.join(objdir, base[:-3] + ".o")
         return os.path.join(OBJDIR, base[:-3] + ".o")
 
+    # a library that is newer than every source it is built from is up to date even when the object files are not
+    # there (build/ does not travel to the GPU box; the in-tree .so does): nothing to compile, nothing to link
+    all_deps = sources + headers
+    if variant is None and not force and os.path.exists(lib) and not _newer(lib, all_deps):
+        build_host(lib, verbose)
+        build_lts_host(lib, verbose)
+        return lib
     for src in sources:
         obj = obj_of(src)
         if force or _newer(obj, [src] + _includes(src)):
