@@ -112,6 +112,23 @@ def test_plane_wave_cuda(built_library, order, dt, bar):
     err = np.linalg.norm(Bs.l2_error(order, coords, got.astype(np.float64), lambda x: f(x, t_end)))
     ref = np.linalg.norm(Bs.l2_error(order, coords, 0 * got.astype(np.float64), lambda x: f(x, t_end)))
     assert err / ref < (2e-2 if order == 4 else 2e-3)
+    # energy output on the device (ssb_volume_energies): equals the oracle's quadrature formulation, and has the physics of
+    # a travelling plane wave -- kinetic = strain energy (equipartition), total energy conserved up to the (tiny) upwind
+    # dissipation, momentum of a full period = 0
+    N = got.shape[0]
+    vol = np.abs(np.linalg.det(coords[:, 1:] - coords[:, :1])) / 6.0
+    mat = np.tile(np.array([LAM, MU, RHO]), (N, 1))
+    dev = data.dofs.device
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    ctx.volume_energies(api.strided(data.dofs), torch.from_numpy(vol).to(dev),
+                        torch.from_numpy(mat).to(dev), N, out)
+    e = out.cpu().numpy()
+    want_e = O.volume_energies(order, got.astype(np.float64), vol, mat)
+    assert np.all(np.abs(e[:7] - want_e[:7]) <= 1e-6 * np.abs(want_e[:2]).max())
+    e0 = O.volume_energies(order, d["Q"].astype(np.float64), vol, mat)
+    assert abs(e[0] - e[1]) < 2e-3 * (e[0] + e[1])
+    assert 0.995 < (e[0] + e[1]) / (e0[0] + e0[1]) < 1.0 + 1e-5
+    assert np.all(np.abs(e[4:7]) < 1e-6 * np.sqrt(e[0]))
 
 
 def test_plane_wave_lts():
