@@ -148,6 +148,40 @@ class Local {
           "ssb_local");
   }
 
+  // Boundary faces with a nodal boundary condition (the second half of Local::computeBatchedIntegral, Local.cpp:350-395,
+  // through DirichletBoundary::evaluateOnDevice): one face list (cell, face, FaceType) for Dirichlet (4) and
+  // FreeSurfaceGravity (2) faces; all arrays are device arrays (include/seissol_b200.h, ssb_local_nodal_bc).
+  struct BoundaryFaces {
+    const long long* cell{nullptr};
+    const std::uint8_t* face{nullptr};
+    const std::uint8_t* kind{nullptr};
+    const void* tinv{nullptr};            // [m][9][9]
+    const void* easiMap{nullptr};         // [m][9][9][B2]
+    const void* easiConstant{nullptr};    // [m][9][B2]
+    const void* displacement{nullptr};    // [m][B2]
+    const void* rhoG{nullptr};            // [m]
+    std::size_t size{0};
+  };
+  void computeBatchedNodalBoundaryConditions(Layer& layer, const BoundaryFaces& bc, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_local_nodal_bc(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs),
+                             strided(layer.buffers, layer.dofsStride * rs), strided(layer.neighboringIntegration, 324 * rs),
+                             bc.cell, bc.face, bc.kind, bc.tinv, bc.easiMap, bc.easiConstant, bc.displacement, bc.rhoG,
+                             static_cast<long long>(bc.size), stream),
+          "ssb_local_nodal_bc");
+  }
+  // Local::evaluateBatchedTimeDependentBc (Local.cpp:397-455): FaceType::Analytical faces.  The host loop that evaluates
+  // the analytical solution at the face nodes and integrates it over the time step stays with the caller (it runs user
+  // callbacks); analyticScratch is its result on the device, [m][9][B2].
+  void evaluateBatchedTimeDependentBc(Layer& layer, const long long* cells, const std::uint8_t* faces,
+                                      const void* analyticScratch, std::size_t numFaces, cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_local_nodal_flux(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs),
+                               strided(layer.neighboringIntegration, 324 * rs), cells, faces, analyticScratch,
+                               static_cast<long long>(numFaces), stream),
+          "ssb_local_nodal_flux");
+  }
+
   private:
   Context& ctx_;
 };
@@ -272,4 +306,24 @@ class DynamicRupture {
 };
 
 }  // namespace kernels
+
+// Volume part of writer::EnergyOutput::computeVolumeEnergies (src/ResultWriter/EnergyOutput.cpp:347-486): the OpenMP loop
+// over the cells of a layer as one launch.  volumes [size] and materials [size][3] = lambda, mu, rho are device arrays of
+// doubles; energies is a device double[8] the caller zeroes before the first layer and reads back after the last
+// (elastic kinetic, elastic, acoustic kinetic, acoustic, momentum x / y / z, unused).
+class EnergyOutput {
+  public:
+  explicit EnergyOutput(Context& ctx) : ctx_(ctx) {}
+  void computeVolumeEnergies(Layer& layer, const double* volumes, const double* materials, double* energies,
+                             cudaStream_t stream) {
+    const std::size_t rs = layer.realSize;
+    check(ssb_volume_energies(ctx_.handle(), strided(layer.dofs, layer.dofsStride * rs), volumes, materials,
+                              static_cast<long long>(layer.size), energies, stream),
+          "ssb_volume_energies");
+  }
+
+  private:
+  Context& ctx_;
+};
+
 }  // namespace seissol_b200
