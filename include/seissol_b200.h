@@ -302,6 +302,18 @@ int ssb_local_nodal_flux(ssb_ctx* ctx, ssb_array_t dofs, ssb_array_t neigh_int, 
 int ssb_volume_energies(ssb_ctx* ctx, ssb_array_t dofs, const double* volume, const double* material, long long n,
                         double* out, void* stream);
 
+/* Fault part of the energy output (EnergyOutput::computeDynamicRuptureEnergies, src/ResultWriter/EnergyOutput.cpp:262-345)
+ * for m fault faces: total frictional work = sum of DREnergyOutput::frictionalEnergy over the points, potency = sum over
+ * the faces of (sum of accumulatedSlip over the points) * 0.5 * doubledSurfaceArea / P, seismic moment = potency
+ * increment * harmonic mean of the two shear moduli.  frictional_energy / accumulated_slip [m][ppad] are the arrays
+ * ssb_friction_* updates (ssb_friction_data_t::frictional_energy, energy_accumulated_slip), doubled_surface_area [m] in the
+ * precision of the context; material_plus / minus [m][3] = lambda, mu, rho (doubles, as for ssb_setup_dr_matrices);
+ * plus_side_on_this_rank [m] or NULL (all faces).  out: DEVICE double[4], ACCUMULATED: [0] total frictional work, [1]
+ * potency, [2] seismic moment, [3] unused (the static frictional work, computeStaticWork, is not covered). */
+int ssb_fault_energies(ssb_ctx* ctx, const void* frictional_energy, const void* accumulated_slip,
+                       const void* doubled_surface_area, const double* material_plus, const double* material_minus,
+                       const uint8_t* plus_side_on_this_rank, long long m, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Set-up on the device (elastic): the per-element and per-fault-face matrices the entry points above consume, from
  * vertex coordinates and material parameters; all inputs are DEVICE arrays of doubles, results are stored in the

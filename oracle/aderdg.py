@@ -310,6 +310,21 @@ def volume_energies(order, Q, volume, material):
     return out
 
 
+def fault_energies(points, frictional_energy, accumulated_slip, doubled_surface_area, mu_plus, mu_minus, on_rank=None):
+    """EnergyOutput::computeDynamicRuptureEnergies (src/ResultWriter/EnergyOutput.cpp:295-324) without the static work:
+    per-point arrays [m, ppad] (only the first `points` entries count).  Returns [frictional work, potency, moment]."""
+    out = np.zeros(3)
+    for i in range(frictional_energy.shape[0]):
+        if on_rank is not None and not on_rank[i]:
+            continue
+        out[0] += np.sum(frictional_energy[i, :points].astype(np.float64))
+        mu = 2.0 * mu_plus[i] * mu_minus[i] / (mu_plus[i] + mu_minus[i])
+        inc = np.sum(accumulated_slip[i, :points].astype(np.float64)) * 0.5 * float(doubled_surface_area[i]) / points
+        out[1] += inc
+        out[2] += inc * mu
+    return out
+
+
 def dr_interpolate(tab, ders_plus, ders_minus, tinvT, face_info, coeffs):
     """DynamicRupture::spaceTimeInterpolation (src/Kernels/DynamicRupture.cpp:57-108):
     for each time point s: Q±(t_s) = sum_d coeffs[s,d] dQ±(d);

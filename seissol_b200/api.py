@@ -19,7 +19,7 @@ SYMBOLS = [
     "ssb_local_faceproj", "ssb_ader_local_faceproj", "ssb_neigh_faceproj", "ssb_taylor_faceproj", "ssb_accumulate_rows",
     "ssb_set_dr_layout", "ssb_dr_interp", "ssb_friction_lsw", "ssb_friction_rsfvw", "ssb_neigh_dr",
     "ssb_visco_ader", "ssb_visco_local", "ssb_visco_neigh", "ssb_visco_neigh_dr",
-    "ssb_setup_cell_matrices", "ssb_setup_dr_matrices", "ssb_local_nodal_bc", "ssb_local_nodal_flux", "ssb_volume_energies",
+    "ssb_setup_cell_matrices", "ssb_setup_dr_matrices", "ssb_local_nodal_bc", "ssb_local_nodal_flux", "ssb_volume_energies", "ssb_fault_energies",
     "ssb_error_string", "ssb_version",
 ]
 
@@ -103,6 +103,7 @@ def load_library():
     lib.ssb_local_nodal_bc.argtypes = [P, A, A, A, P, P, P, P, P, P, P, P, LL, P]
     lib.ssb_local_nodal_flux.argtypes = [P, A, A, P, P, P, LL, P]
     lib.ssb_volume_energies.argtypes = [P, A, P, P, LL, P, P]
+    lib.ssb_fault_energies.argtypes = [P, P, P, P, P, P, P, LL, P, P]
     lib.ssb_setup_cell_matrices.argtypes = [P, P, P, P, P, A, A, LL, P]
     lib.ssb_setup_dr_matrices.argtypes = [P, P, P, P, P, P, P, P, P, P, P, LL, P]
     _lib = lib
@@ -274,6 +275,13 @@ class Context:
         """Energy output of the volume: out[8] (f64 device tensor, accumulated) += kinetic / elastic / acoustic energies
         and momentum of n elements; volume [n], material [n, 3] = lambda, mu, rho (f64 device tensors)."""
         _check(self.lib.ssb_volume_energies(self.handle, dofs, _ptr(volume), _ptr(material), n, _ptr(out), _stream(stream)))
+
+    def fault_energies(self, frictional_energy, accumulated_slip, doubled_surface_area, material_plus, material_minus, m,
+                       out, plus_side_on_this_rank=None, stream=None):
+        """Energy output of the fault: out[4] (f64 device tensor, accumulated) += frictional work, potency, seismic moment."""
+        _check(self.lib.ssb_fault_energies(self.handle, _ptr(frictional_energy), _ptr(accumulated_slip),
+                                           _ptr(doubled_surface_area), _ptr(material_plus), _ptr(material_minus),
+                                           _ptr(plus_side_on_this_rank), m, _ptr(out), _stream(stream)))
 
     # -- set-up on the device --------------------------------------------------------------------
     def setup_cell_matrices(self, coords, neighbors, material, face_types, local_int, neigh_int, n, stream=None):

@@ -85,6 +85,8 @@ struct SetupCellParams;
 struct SetupDrParams;
 int setupCellEntry(const SetupCellParams&, int realSize, cudaStream_t);
 int setupDrEntry(const SetupDrParams&, int realSize, cudaStream_t);
+struct FaultEnergyParams;
+int faultEnergiesEntry(const FaultEnergyParams&, int realSize, cudaStream_t);
 
 struct DrKernelSet {
   int order;

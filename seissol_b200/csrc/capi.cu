@@ -866,6 +866,32 @@ int ssb_volume_energies(ssb_ctx* c, ssb_array_t dofs, const double* volume, cons
   return c->ks->volumeEnergies(p, static_cast<cudaStream_t>(stream));
 }
 
+int ssb_fault_energies(ssb_ctx* c, const void* frictional_energy, const void* accumulated_slip,
+                       const void* doubled_surface_area, const double* material_plus, const double* material_minus,
+                       const uint8_t* plus_side_on_this_rank, long long m, double* out, void* stream) {
+  if (c == nullptr || m < 0 || c->equation != 0) {
+    return SSB_EINVAL;
+  }
+  if (m == 0) {
+    return 0;
+  }
+  if (frictional_energy == nullptr || accumulated_slip == nullptr || doubled_surface_area == nullptr ||
+      material_plus == nullptr || material_minus == nullptr || out == nullptr) {
+    return SSB_EINVAL;
+  }
+  FaultEnergyParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.frictionalEnergy = frictional_energy; p.accumulatedSlip = accumulated_slip;
+  p.doubledSurfaceArea = doubled_surface_area;
+  p.materialPlus = material_plus; p.materialMinus = material_minus;
+  p.plusSideOnThisRank = plus_side_on_this_rank;
+  p.out = out;
+  p.m = m;
+  p.points = (c->order + 1) * (c->order + 1);
+  p.ppad = c->ppad;
+  return faultEnergiesEntry(p, c->realSize, static_cast<cudaStream_t>(stream));
+}
+
 int ssb_setup_cell_matrices(ssb_ctx* c, const double* coords, const long long* neighbors, const double* material,
                             const uint8_t* face_types, ssb_array_t local_int, ssb_array_t neigh_int, long long n, void* stream) {
   if (c == nullptr || n < 0 || c->equation != 0) {

@@ -30,4 +30,20 @@ int setupDrEntry(const SetupDrParams& p, int realSize, cudaStream_t stream) {
   return int(cudaGetLastError());
 }
 
+int faultEnergiesEntry(const FaultEnergyParams& p, int realSize, cudaStream_t stream) {
+  if (p.m <= 0) {
+    return 0;
+  }
+  long long blocks = (p.m + 7) / 8;
+  if (blocks > 148LL * 8) {
+    blocks = 148LL * 8;
+  }
+  if (realSize == 4) {
+    k_fault_energies<float><<<unsigned(blocks), 256, 0, stream>>>(p);
+  } else {
+    k_fault_energies<double><<<unsigned(blocks), 256, 0, stream>>>(p);
+  }
+  return int(cudaGetLastError());
+}
+
 }  // namespace ssb

@@ -40,6 +40,66 @@ struct SetupDrParams {
   long long m;
 };
 
+// Fault part of the energy output: EnergyOutput::computeDynamicRuptureEnergies (src/ResultWriter/EnergyOutput.cpp:262-345)
+struct FaultEnergyParams {
+  const void* frictionalEnergy;     // [m][ppad] DREnergyOutput::frictionalEnergy
+  const void* accumulatedSlip;      // [m][ppad] DREnergyOutput::accumulatedSlip
+  const void* doubledSurfaceArea;   // [m]
+  const double* materialPlus;       // [m][3] lambda, mu, rho
+  const double* materialMinus;
+  const uint8_t* plusSideOnThisRank;  // [m] or null (= all faces)
+  double* out;                      // [4] accumulated: frictional work, potency, seismic moment, unused
+  long long m;
+  int points, ppad;
+};
+
+// one warp per fault face, lanes over the points; sums in double
+template <typename R>
+__global__ void __launch_bounds__(256) k_fault_energies(const FaultEnergyParams p) {
+  __shared__ double sAcc[8][3];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double work = 0, potency = 0, moment = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * 8 + warp; i < p.m; i += stride) {
+    if (p.plusSideOnThisRank != nullptr && p.plusSideOnThisRank[i] == 0) {
+      continue;   // warp-uniform
+    }
+    const R* const fe = static_cast<const R*>(p.frictionalEnergy) + i * p.ppad;
+    const R* const as = static_cast<const R*>(p.accumulatedSlip) + i * p.ppad;
+    double w = 0, s = 0;
+    for (int k = lane; k < p.points; k += 32) {
+      w += static_cast<double>(fe[k]);
+      s += static_cast<double>(as[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w += __shfl_xor_sync(0xffffffffu, w, o);
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) {
+      const double muPlus = p.materialPlus[3 * i + 1], muMinus = p.materialMinus[3 * i + 1];
+      const double mu = 2.0 * muPlus * muMinus / (muPlus + muMinus);
+      const double inc = s * 0.5 * static_cast<double>(static_cast<const R*>(p.doubledSurfaceArea)[i]) / p.points;
+      work += w;
+      potency += inc;
+      moment += inc * mu;
+    }
+  }
+  if (lane == 0) {
+    sAcc[warp][0] = work; sAcc[warp][1] = potency; sAcc[warp][2] = moment;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) {
+      t += sAcc[wv][threadIdx.x];
+    }
+    atomicAdd(p.out + threadIdx.x, t);
+  }
+}
+
 namespace setup {
 
 struct M9 {

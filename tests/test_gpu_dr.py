@@ -514,3 +514,34 @@ def test_all_dr_friction_n_steps(gpu, law, order, dt, n, m):
         assert np.linalg.norm(gotk - want) / scale < bar_state, (
             k, np.linalg.norm(gotk - want) / scale, int((dev_abs > 1e-3 * np.abs(want).max()).sum()),
             [(int(a), int(b), float(gotk[a, b]), float(want[a, b])) for a, b in zip(*worst)])
+
+
+@pytest.mark.parametrize("order,dt", [(4, np.float32), (6, np.float32), (6, np.float64)])
+def test_fault_energies(gpu, order, dt):
+    """ssb_fault_energies against the oracle's restatement of EnergyOutput::computeDynamicRuptureEnergies (frictional
+    work, potency, seismic moment); padded points must not count, faces of other ranks are left out."""
+    torch, api, proxy = gpu
+    ctx = api.Context(order, np.dtype(dt).itemsize)
+    m, P = 777, (order + 1) ** 2
+    ppad = ctx.ppad
+    assert ppad >= P
+    rng = np.random.default_rng(3)
+    fe = rng.uniform(0, 2, (m, ppad)).astype(dt)
+    acc = rng.uniform(0, 1, (m, ppad)).astype(dt)
+    fe[:, P:] = 1e30          # padding must be ignored
+    acc[:, P:] = 1e30
+    area = rng.uniform(0.5, 2, m).astype(dt)
+    matp = np.stack([rng.uniform(1, 3, m), rng.uniform(0.5, 2, m), rng.uniform(1, 3, m)], -1)
+    matm = np.stack([rng.uniform(1, 3, m), rng.uniform(0.5, 2, m), rng.uniform(1, 3, m)], -1)
+    on = (rng.uniform(size=m) < 0.8).astype(np.uint8)
+    want = O.fault_energies(P, fe, acc, area, matp[:, 1], matm[:, 1], on)
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to("cuda")  # noqa: E731
+    out = torch.zeros(4, dtype=torch.float64, device="cuda")
+    ctx.fault_energies(d(fe), d(acc), d(area), d(matp), d(matm), m, out, plus_side_on_this_rank=d(on))
+    got = out.cpu().numpy()
+    assert np.all(np.abs(got[:3] - want) <= 1e-12 * np.abs(want)), (got, want)
+    out.zero_()
+    ctx.fault_energies(d(fe), d(acc), d(area), d(matp), d(matm), m, out)
+    want_all = O.fault_energies(P, fe, acc, area, matp[:, 1], matm[:, 1])
+    assert np.all(np.abs(out.cpu().numpy()[:3] - want_all) <= 1e-12 * np.abs(want_all))
+    assert api.load_library().ssb_fault_energies(ctx.handle, None, None, None, None, None, None, 4, None, None) == -1
